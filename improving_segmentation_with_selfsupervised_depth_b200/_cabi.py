@@ -1,0 +1,104 @@
+"""ctypes binding of libsegsde_b200.so (the C-ABI declared in include/segsde_b200.h).
+
+The product path has no CPU fallback: if the library is missing or a call fails, a Python
+exception is raised (reference convention: plain exceptions, e.g. models/__init__.py:23).
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsegsde_b200.so")
+
+
+class SegsdeError(RuntimeError):
+    pass
+
+
+class NHWC(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+                ("c", C.c_int32), ("sn", C.c_int64), ("sh", C.c_int64), ("sw", C.c_int64)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [("kh", C.c_int32), ("kw", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
+                ("dil", C.c_int32), ("pad_mode", C.c_int32), ("up1", C.c_int32), ("act", C.c_int32),
+                ("nchw_norm_in", C.c_int32)]
+
+
+class ReprojArgs(C.Structure):
+    _fields_ = [("tgt", C.c_void_p), ("src", C.c_void_p * 2), ("disp", C.c_void_p),
+                ("K", C.c_void_p), ("inv_K", C.c_void_p), ("T", C.c_void_p * 2),
+                ("noise", C.c_void_p), ("seed", C.c_uint64), ("offset", C.c_uint64),
+                ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("hs", C.c_int32),
+                ("ws", C.c_int32), ("F", C.c_int32), ("min_depth", C.c_float),
+                ("max_depth", C.c_float), ("flags", C.c_int32),
+                ("loss_partial", C.c_void_p), ("ident_sel", C.c_void_p), ("gdisp", C.c_void_p),
+                ("gT_partial", C.c_void_p)]
+
+
+ACT_NONE, ACT_RELU, ACT_ELU, ACT_SIGMOID = 0, 1, 2, 3
+PAD_ZERO, PAD_REFLECT = 0, 1
+REPROJ_NO_SSIM, REPROJ_AVG, REPROJ_NO_AUTOMASK = 1, 2, 4
+E_UNSUPPORTED = -3
+
+_lib = None
+
+
+def lib():
+    """Loads the shared library once. Raises SegsdeError when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SegsdeError(
+                "libsegsde_b200.so not found at %s — run `python -c 'import __graft_entry__ as g; "
+                "g.build()'` (there is no CPU / PyTorch fallback for the hot path)" % LIB_PATH)
+        _lib = C.CDLL(LIB_PATH)
+        _lib.segsde_version.restype = C.c_char_p
+        _lib.segsde_error_string.restype = C.c_char_p
+        _lib.segsde_launch_count.restype = C.c_int64
+    return _lib
+
+
+def check(code, what=""):
+    if code != 0:
+        msg = lib().segsde_error_string(C.c_int(code)).decode()
+        raise SegsdeError("%s failed (%d): %s" % (what, code, msg))
+
+
+def call(name, *args):
+    """Calls an int-returning entry point and raises on a non-zero code."""
+    fn = getattr(lib(), name)
+    code = fn(*args)
+    if code != 0:
+        check(code, name)
+
+
+def try_call(name, *args):
+    """Like call() but returns False on SEGSDE_E_UNSUPPORTED (shape outside a kernel family)."""
+    code = getattr(lib(), name)(*args)
+    if code == E_UNSUPPORTED:
+        return False
+    if code != 0:
+        check(code, name)
+    return True
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise SegsdeError("segsde_b200 ops run on CUDA tensors only (got a %s tensor); there is "
+                              "no CPU fallback" % t.device)
+
+
+def launch_count():
+    return int(lib().segsde_launch_count())

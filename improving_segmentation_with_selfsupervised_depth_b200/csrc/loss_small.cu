@@ -1,0 +1,256 @@
+// Edge-aware smoothness (monodepth_layers.py:208-221 + mean normalisation monodepth_loss.py:182-184),
+// segmentation cross-entropy (loss/loss.py:17-37) and the axpby used to scale stored unit gradients.
+#include "common.cuh"
+
+namespace segsde {
+
+// ---- smoothness -------------------------------------------------------------------------------
+__global__ void smooth_mean_kernel(const float* __restrict__ disp, int hw, float* __restrict__ mean_out) {
+  // one block per sample; fixed-order reduction (deterministic)
+  const int b = blockIdx.x;
+  const float* d = disp + (size_t)b * hw;
+  double a = 0.0;
+  for (int i = threadIdx.x; i < hw; i += blockDim.x) a += (double)d[i];
+  __shared__ double sh[32];
+  a = warp_sum_d(a);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh[i];
+    mean_out[b] = (float)(t / (double)hw);
+  }
+}
+
+// loss terms:  Lx = sum |dhat[x]-dhat[x+1]| * exp(-mean_c |I[x]-I[x+1]|),  Ly likewise;
+// ghat = d(Lx/cnt_x + Ly/cnt_y)/d dhat   (cnt_x = B*h*(w-1), cnt_y = B*(h-1)*w)
+__global__ void smooth_fused_kernel(const float* __restrict__ disp, const float* __restrict__ img,
+                                    const float* __restrict__ mean, int B, int h, int w,
+                                    float* __restrict__ acc, float* __restrict__ ghat) {
+  const int b = blockIdx.z;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const size_t hw = (size_t)h * w;
+  const float inv_m = 1.f / (mean[b] + 1e-7f);
+  const float* d = disp + b * hw;
+  const float* I = img + (size_t)b * 3 * hw;
+  float lx = 0.f, ly = 0.f, g = 0.f, dot = 0.f;
+  if (x < w && y < h) {
+    const size_t o = (size_t)y * w + x;
+    const float dc = d[o] / (mean[b] + 1e-7f);
+    const float wx_cnt = 1.f / ((float)B * (float)h * (float)(w - 1));
+    const float wy_cnt = 1.f / ((float)B * (float)(h - 1) * (float)w);
+    // edge (x, x+1): this pixel is the left end
+    if (x + 1 < w) {
+      const float dn = d[o + 1] / (mean[b] + 1e-7f);
+      float gi = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) gi += fabsf(I[c * hw + o] - I[c * hw + o + 1]);
+      const float e = expf(-(gi / 3.f));
+      const float df = dc - dn;
+      lx = fabsf(df) * e * wx_cnt;
+      g += (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f)) * e * wx_cnt;
+    }
+    if (x > 0) {  // edge (x-1, x): right end
+      const float dp = d[o - 1] / (mean[b] + 1e-7f);
+      float gi = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) gi += fabsf(I[c * hw + o - 1] - I[c * hw + o]);
+      const float e = expf(-(gi / 3.f));
+      const float df = dp - dc;
+      g -= (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f)) * e * wx_cnt;
+    }
+    if (y + 1 < h) {
+      const float dn = d[o + w] / (mean[b] + 1e-7f);
+      float gi = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) gi += fabsf(I[c * hw + o] - I[c * hw + o + w]);
+      const float e = expf(-(gi / 3.f));
+      const float df = dc - dn;
+      ly = fabsf(df) * e * wy_cnt;
+      g += (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f)) * e * wy_cnt;
+    }
+    if (y > 0) {
+      const float dp = d[o - w] / (mean[b] + 1e-7f);
+      float gi = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) gi += fabsf(I[c * hw + o - w] - I[c * hw + o]);
+      const float e = expf(-(gi / 3.f));
+      const float df = dp - dc;
+      g -= (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f)) * e * wy_cnt;
+    }
+    if (ghat) ghat[b * hw + o] = g;
+    dot = g * d[o];
+    (void)inv_m;
+  }
+  __shared__ float sh[3][8];
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  lx = warp_sum(lx); ly = warp_sum(ly); dot = warp_sum(dot);
+  if ((tid & 31) == 0) { sh[0][tid >> 5] = lx; sh[1][tid >> 5] = ly; sh[2][tid >> 5] = dot; }
+  __syncthreads();
+  if (tid < 3) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += sh[tid][i];
+    atomicAdd(tid < 2 ? acc + tid : acc + 2 + b, t);
+  }
+}
+
+// d dhat_i / d d_j = delta_ij/(m+eps) - d_i/((m+eps)^2 hw)
+__global__ void smooth_grad_finalize_kernel(const float* __restrict__ ghat, const float* __restrict__ mean,
+                                            const float* __restrict__ acc, int hw, float wgt,
+                                            float* __restrict__ gdisp) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= hw) return;
+  const float me = mean[b] + 1e-7f;
+  const float dot = acc[2 + b];
+  gdisp[(size_t)b * hw + i] += wgt * (ghat[(size_t)b * hw + i] / me - dot / (me * me * (float)hw));
+}
+
+__global__ void axpby_kernel(const float* __restrict__ x, float a, float* __restrict__ y, int accumulate,
+                             long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) y[i] = accumulate ? y[i] + a * x[i] : a * x[i];
+}
+
+// y (+)= (ca*a[0] + cb*b[0]) * x : scaling by upstream-gradient scalars that live on the device
+__global__ void scale_by_dev_kernel(const float* __restrict__ x, const float* __restrict__ a, float ca,
+                                    const float* __restrict__ b, float cb, float* __restrict__ y,
+                                    int accumulate, long long n) {
+  const float s = (a ? ca * a[0] : 0.f) + (b ? cb * b[0] : 0.f);
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) y[i] = accumulate ? y[i] + s * x[i] : s * x[i];
+}
+
+// out[s] = reproj[s] + wsm[s]*(sacc[s][0]+sacc[s][1]);  out[S] = mean_s out[s]
+struct CombineW { float w[8]; };
+__global__ void mono_combine_kernel(const float* __restrict__ reproj, const float* __restrict__ sacc,
+                                    int S, int sacc_stride, CombineW wsm, float* __restrict__ out) {
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int s = 0; s < S; ++s) {
+      const float l = reproj[s] + wsm.w[s] * (sacc[s * sacc_stride] + sacc[s * sacc_stride + 1]);
+      out[s] = l; tot += l;
+    }
+    out[S] = tot / (float)S;
+  }
+}
+
+// ---- cross entropy ----------------------------------------------------------------------------
+// One thread per pixel; the C logits of a pixel are contiguous (NHWC view), C is small (19).
+template <bool BWD>
+__global__ void ce_kernel(View lg, const long long* __restrict__ target, const float* __restrict__ pw,
+                          int ignore_index, float* __restrict__ acc, const float* __restrict__ gscale,
+                          View dl) {
+  const long long npix = (long long)lg.n * lg.h * lg.w;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float nll = 0.f, valid = 0.f;
+  if (i < npix) {
+    const int x = (int)(i % lg.w);
+    const int y = (int)((i / lg.w) % lg.h);
+    const int n = (int)(i / ((long long)lg.w * lg.h));
+    const float* p = lg.p + lg.off(n, y, x);
+    const long long t = target[i];
+    const bool ok = (t != ignore_index);
+    const int C = lg.c;
+    float mx = -3.4e38f;
+    for (int c = 0; c < C; ++c) mx = fmaxf(mx, p[c]);
+    float se = 0.f;
+    for (int c = 0; c < C; ++c) se += expf(p[c] - mx);
+    const float lse = mx + logf(se);
+    const float wgt = pw ? pw[i] : 1.f;
+    if (!BWD) {
+      if (ok) { nll = (lse - p[t]) * wgt; valid = 1.f; }
+    } else {
+      float* g = dl.p + dl.off(n, y, x);
+      const float s = ok ? gscale[0] * wgt : 0.f;
+      for (int c = 0; c < C; ++c) {
+        const float sm = expf(p[c] - lse);
+        g[c] = s * (sm - ((long long)c == t ? 1.f : 0.f));
+      }
+    }
+  }
+  if (!BWD) {
+    __shared__ float sh[2][8];
+    nll = warp_sum(nll); valid = warp_sum(valid);
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = nll; sh[1][threadIdx.x >> 5] = valid; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      float t = 0.f;
+      for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += sh[threadIdx.x][k];
+      atomicAdd(acc + threadIdx.x, t);
+    }
+  }
+}
+
+}  // namespace segsde
+using namespace segsde;
+
+extern "C" int segsde_smooth_mean(const float* disp, int B, int h, int w, float* mean_out, void* stream) {
+  if (!disp || !mean_out || B < 1 || h < 1 || w < 1) return SEGSDE_E_ARG;
+  smooth_mean_kernel<<<B, 1024, 0, as_stream(stream)>>>(disp, h * w, mean_out);
+  return launched();
+}
+extern "C" int segsde_smooth_fused(const float* disp, const float* img, const float* mean, int B, int h,
+                                   int w, float* acc, float* ghat, void* stream) {
+  if (!disp || !img || !mean || !acc || B < 1 || h < 2 || w < 2) return SEGSDE_E_ARG;
+  dim3 block(32, 8), grid(cdiv(w, 32), cdiv(h, 8), B);
+  smooth_fused_kernel<<<grid, block, 0, as_stream(stream)>>>(disp, img, mean, B, h, w, acc, ghat);
+  return launched();
+}
+extern "C" int segsde_smooth_grad_finalize(const float* ghat, const float* mean, const float* acc, int B,
+                                           int h, int w, float wgt, float* gdisp, void* stream) {
+  if (!ghat || !mean || !acc || !gdisp) return SEGSDE_E_ARG;
+  dim3 grid(cdiv((int64_t)h * w, 256), B);
+  smooth_grad_finalize_kernel<<<grid, 256, 0, as_stream(stream)>>>(ghat, mean, acc, h * w, wgt, gdisp);
+  return launched();
+}
+extern "C" int segsde_axpby(const float* x, float a, float* y, int accumulate, int64_t n, void* stream) {
+  if (!x || !y || n < 0) return SEGSDE_E_ARG;
+  if (n == 0) return SEGSDE_OK;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  axpby_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x, a, y, accumulate, (long long)n);
+  return launched();
+}
+
+extern "C" int segsde_scale_by_dev(const float* x, const float* a, float ca, const float* b, float cb,
+                                   float* y, int accumulate, int64_t n, void* stream) {
+  if (!x || !y || n < 0) return SEGSDE_E_ARG;
+  if (n == 0) return SEGSDE_OK;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  scale_by_dev_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x, a, ca, b, cb, y, accumulate, (long long)n);
+  return launched();
+}
+extern "C" int segsde_mono_combine(const float* reproj, const float* sacc, int S, int sacc_stride,
+                                   const float* smooth_w_host, float* out, void* stream) {
+  if (!reproj || !sacc || !smooth_w_host || !out || S < 1 || S > 8) return SEGSDE_E_ARG;
+  CombineW w;
+  for (int s = 0; s < 8; ++s) w.w[s] = s < S ? smooth_w_host[s] : 0.f;
+  mono_combine_kernel<<<1, 32, 0, as_stream(stream)>>>(reproj, sacc, S, sacc_stride, w, out);
+  return launched();
+}
+
+extern "C" int segsde_ce_fwd(const segsde_nhwc_t* logits, const int64_t* target, const float* pixel_w,
+                             int ignore_index, float* acc, void* stream) {
+  if (!logits || !logits->ptr || !target || !acc) return SEGSDE_E_ARG;
+  View lg = mk(logits), none = mk(nullptr);
+  const long long npix = (long long)lg.n * lg.h * lg.w;
+  ce_kernel<false><<<cdiv(npix, 256), 256, 0, as_stream(stream)>>>(
+      lg, (const long long*)target, pixel_w, ignore_index, acc, nullptr, none);
+  return launched();
+}
+extern "C" int segsde_ce_bwd(const segsde_nhwc_t* logits, const int64_t* target, const float* pixel_w,
+                             int ignore_index, const float* gscale_dev, const segsde_nhwc_t* dlogits,
+                             void* stream) {
+  if (!logits || !logits->ptr || !target || !gscale_dev || !dlogits || !dlogits->ptr) return SEGSDE_E_ARG;
+  View lg = mk(logits), dl = mk(dlogits);
+  if (!same_shape(lg, dl)) return SEGSDE_E_ARG;
+  const long long npix = (long long)lg.n * lg.h * lg.w;
+  ce_kernel<true><<<cdiv(npix, 256), 256, 0, as_stream(stream)>>>(
+      lg, (const long long*)target, pixel_w, ignore_index, nullptr, gscale_dev, dl);
+  return launched();
+}

@@ -1,0 +1,262 @@
+/*
+ * segsde_b200.h — C-ABI of the B200-native monodepth / joint-segmentation hot path.
+ *
+ * The reference (lhoyer/improving_segmentation_with_selfsupervised_depth) has no FFI: its
+ * hot path is the Python surface of models/ and loss/ executing stock ATen/cuDNN ops.  Each
+ * entry point below replaces the ATen op sequence at the cited reference location; the Python
+ * mirror of models/ and loss/ (package improving_segmentation_with_selfsupervised_depth_b200)
+ * binds them with ctypes.  See INTEGRATION.md for the binding a maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - activations are "NHWC views": channel stride 1, explicit element strides for n/h/w
+ *     (so halo-padded buffers and channel slices of concat buffers are expressible);
+ *   - image-like loss inputs (colour frames, disparities) stay in the reference's NCHW planar
+ *     layout (loader contract, sequence_segmentation_loader.py:183-250);
+ *   - weights are O,kh,kw,I ("OHWI") fp32 = an OIHW torch tensor in channels_last memory format;
+ *   - every call takes the cudaStream_t to launch on (as void*), never allocates, never syncs;
+ *   - return value: 0 = ok, <0 = argument error (SEGSDE_E_*), >0 = cudaError_t of the launch.
+ */
+#ifndef SEGSDE_B200_H
+#define SEGSDE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SEGSDE_OK 0
+#define SEGSDE_E_ARG (-1)       /* bad shape / null pointer / unsupported flag combination */
+#define SEGSDE_E_ALIGN (-2)     /* pointer or stride not aligned as the kernel requires */
+#define SEGSDE_E_UNSUPPORTED (-3)
+#define SEGSDE_E_WORKSPACE (-4) /* workspace too small */
+
+/* NHWC view: element (n,h,w,c) lives at ptr[n*sn + h*sh + w*sw + c]. */
+typedef struct {
+  void* ptr;
+  int32_t n, h, w, c;
+  int64_t sn, sh, sw;
+} segsde_nhwc_t;
+
+/* activation codes (conv epilogue / act backward) */
+enum { SEGSDE_ACT_NONE = 0, SEGSDE_ACT_RELU = 1, SEGSDE_ACT_ELU = 2, SEGSDE_ACT_SIGMOID = 3 };
+/* padding modes */
+enum { SEGSDE_PAD_ZERO = 0, SEGSDE_PAD_REFLECT = 1 };
+
+const char* segsde_version(void);
+/* Human-readable text for a return code (static storage). */
+const char* segsde_error_string(int code);
+/* Number of kernel launches issued through this library since load (all streams). */
+int64_t segsde_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Convolution (replaces nn.Conv2d / Conv3x3+ReflectionPad2d / upsample+cat feeding a conv:
+ * models/monodepth_layers.py:127-142, models/depth_decoder.py:93-101, torchvision resnet blocks
+ * used by models/resnet_encoder.py:90-101, models/pose_decoder.py:30-33, models/model_parts.py:9-25)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t kh, kw, stride, pad, dil;
+  int32_t pad_mode;     /* SEGSDE_PAD_* */
+  int32_t up1;          /* 1: source 1 is nearest-upsampled x2 on the fly (depth_decoder.py:93-96) */
+  int32_t act;          /* SEGSDE_ACT_* fused after bias */
+  int32_t nchw_norm_in; /* 1: x1.ptr is an NCHW planar image and (x-0.45)/0.225 is applied on load
+                           (resnet_encoder.py:92); x1 strides are then ignored */
+} segsde_conv_desc_t;
+
+/* y = act(conv(cat(x1[up], x2), w) + bias).  x2 may be NULL (c=0).  bias may be NULL.
+ * w: [Cout][kh][kw][C1+C2] fp32.  Generic CUDA-core path: any shape. */
+int segsde_conv2d_fwd(const segsde_nhwc_t* x1, const segsde_nhwc_t* x2, const float* w,
+                      const float* bias, const segsde_nhwc_t* y, const segsde_conv_desc_t* d,
+                      void* stream);
+/* dx{1,2} = conv_transpose(dy, w), folded through reflect padding / upsampling / the concat split.
+ * Either dx may be NULL (source needs no gradient). dx buffers must be zero-filled by the caller
+ * when d->pad_mode==REFLECT or d->up1 (folding accumulates with atomics). */
+int segsde_conv2d_dgrad(const segsde_nhwc_t* dy, const float* w, const segsde_nhwc_t* dx1,
+                        const segsde_nhwc_t* dx2, const segsde_conv_desc_t* d, void* stream);
+/* dw += sum_pixels dy (x) patch(x) ; dbias += sum_pixels dy.  dw/dbias must be zero-filled (or hold
+ * a running gradient) — split-K partial sums are accumulated with atomics. dbias may be NULL. */
+int segsde_conv2d_wgrad(const segsde_nhwc_t* x1, const segsde_nhwc_t* x2, const segsde_nhwc_t* dy,
+                        float* dw, float* dbias, const segsde_conv_desc_t* d, void* stream);
+
+/* Tensor-core (tcgen05/TMEM/TMA, TF32 in / FP32 accumulate) implicit-GEMM path.
+ * Same contract as the generic entry points, restricted shapes; returns SEGSDE_E_UNSUPPORTED when
+ * the shape is outside the family so the caller can route to the generic path. */
+int segsde_conv2d_fwd_tc(const segsde_nhwc_t* x1, const segsde_nhwc_t* x2, const float* w,
+                         const float* bias, const segsde_nhwc_t* y, const segsde_conv_desc_t* d,
+                         void* stream);
+int segsde_conv2d_dgrad_tc(const segsde_nhwc_t* dy, const float* w, const segsde_nhwc_t* dx1,
+                           const segsde_nhwc_t* dx2, const segsde_conv_desc_t* d, void* stream);
+int segsde_conv2d_wgrad_tc(const segsde_nhwc_t* x1, const segsde_nhwc_t* x2,
+                           const segsde_nhwc_t* dy, float* dw, float* dbias,
+                           const segsde_conv_desc_t* d, void* stream);
+/* 1 if this process can run the tensor-core path (driver entry point for tensor maps found). */
+int segsde_tc_available(void);
+
+/* dz = dy * act'(y) computed from the activation OUTPUT y (ReLU/ELU/sigmoid). In-place allowed. */
+int segsde_act_bwd(const segsde_nhwc_t* y, const segsde_nhwc_t* dy, const segsde_nhwc_t* dz, int act,
+                   void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * BatchNorm2d (torchvision blocks, ASPP model_parts.py:11,23, seg head
+ * joint_segmentation_depth_decoder.py:43).  Train mode = batch statistics (biased var for
+ * normalisation, unbiased for the running update, momentum as torch).
+ * ------------------------------------------------------------------------------------------- */
+/* sums[0..C) = sum x, sums[C..2C) = sum x^2 (fp64, must be zero-filled). */
+int segsde_bn_stats(const segsde_nhwc_t* x, double* sums, void* stream);
+/* mean/invstd from sums; running stats update when running_mean != NULL. count = N*H*W. */
+int segsde_bn_finalize(const double* sums, int c, int64_t count, float eps, float momentum,
+                       float* mean, float* invstd, float* running_mean, float* running_var,
+                       void* stream);
+/* invstd from running_var (eval mode): mean=running_mean, invstd=1/sqrt(var+eps). */
+int segsde_bn_eval_prepare(const float* running_mean, const float* running_var, int c, float eps,
+                           float* mean, float* invstd, void* stream);
+/* y = act((x-mean)*invstd*gamma + beta [+ residual]); act in {NONE, RELU}. residual may be NULL. */
+int segsde_bn_apply(const segsde_nhwc_t* x, const float* mean, const float* invstd,
+                    const float* gamma, const float* beta, const segsde_nhwc_t* residual,
+                    const segsde_nhwc_t* y, int act, void* stream);
+/* Backward, step 1: red[0..C)=sum dz, red[C..2C)=sum dz*xhat (fp64, zero-filled) where
+ * dz = dy * relu'(y) (act==RELU needs y). */
+int segsde_bn_bwd_reduce(const segsde_nhwc_t* x, const segsde_nhwc_t* y, const segsde_nhwc_t* dy,
+                         const float* mean, const float* invstd, int act, double* red, void* stream);
+/* Backward, step 2: dx (train: full formula; eval: dz*gamma*invstd), dres = dz (may be NULL),
+ * dgamma/dbeta (+=, may be NULL) from red. */
+int segsde_bn_bwd_apply(const segsde_nhwc_t* x, const segsde_nhwc_t* y, const segsde_nhwc_t* dy,
+                        const float* mean, const float* invstd, const float* gamma, int act,
+                        int training, const double* red, int64_t count, const segsde_nhwc_t* dx,
+                        const segsde_nhwc_t* dres, float* dgamma, float* dbeta, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Pooling / resampling / layout
+ * ------------------------------------------------------------------------------------------- */
+/* MaxPool2d(3, stride 2, pad 1) (resnet_encoder.py:96). idx: uint8 argmax tap per output element. */
+int segsde_maxpool3x3s2_fwd(const segsde_nhwc_t* x, const segsde_nhwc_t* y, uint8_t* idx, void* stream);
+int segsde_maxpool3x3s2_bwd(const segsde_nhwc_t* dy, const uint8_t* idx, const segsde_nhwc_t* dx,
+                            void* stream); /* dx zero-filled by caller */
+/* Spatial mean: y[n,c] = scale * mean_hw x (ASPPPooling, pose_decoder.py:53). y: [N,1,1,C] view. */
+int segsde_spatial_mean_fwd(const segsde_nhwc_t* x, const segsde_nhwc_t* y, float scale, void* stream);
+int segsde_spatial_mean_bwd(const segsde_nhwc_t* dy, const segsde_nhwc_t* dx, float scale, void* stream);
+/* y[n,h,w,c] = x[n,0,0,c] (bilinear resize from 1x1) and its adjoint (sum over h,w). */
+int segsde_broadcast_hw_fwd(const segsde_nhwc_t* x, const segsde_nhwc_t* y, void* stream);
+int segsde_broadcast_hw_bwd(const segsde_nhwc_t* dy, const segsde_nhwc_t* dx, void* stream);
+/* Strided NHWC copy (channel concat into a slice view; layout normalisation). */
+int segsde_copy_nhwc(const segsde_nhwc_t* x, const segsde_nhwc_t* y, void* stream);
+/* y = a + b ; y = a * sigmoid(b) (SelfAttention gate, model_parts.py:43-45) and its backward. */
+int segsde_add(const segsde_nhwc_t* a, const segsde_nhwc_t* b, const segsde_nhwc_t* y, void* stream);
+int segsde_gate_fwd(const segsde_nhwc_t* f, const segsde_nhwc_t* a, const segsde_nhwc_t* y, void* stream);
+int segsde_gate_bwd(const segsde_nhwc_t* f, const segsde_nhwc_t* a, const segsde_nhwc_t* dy,
+                    const segsde_nhwc_t* df, const segsde_nhwc_t* da, void* stream);
+/* NCHW planar (arbitrary strides given in elements) <-> NHWC view. */
+int segsde_nchw_to_nhwc(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw,
+                        const segsde_nhwc_t* y, void* stream);
+int segsde_nhwc_to_nchw(const segsde_nhwc_t* x, float* y, int64_t sn, int64_t sc, int64_t sh,
+                        int64_t sw, void* stream);
+/* Bilinear resize, F.interpolate semantics (align_corners 0/1), multi-channel NHWC. */
+int segsde_bilinear_fwd(const segsde_nhwc_t* x, const segsde_nhwc_t* y, int align_corners, void* stream);
+int segsde_bilinear_bwd(const segsde_nhwc_t* dy, const segsde_nhwc_t* dx, int align_corners,
+                        void* stream); /* dx zero-filled by caller */
+/* Dropout (model_parts.py:25, joint_segmentation_depth_decoder.py:45): mask is generated from a
+ * counter-based Philox stream (seed, offset) unless mask_in != NULL (replay mode: 0/1 floats).
+ * y = x * mask / (1-p); mask_out (uint8, may be NULL) is what backward needs. channelwise=1 is
+ * Dropout2d (monodepth_layers.py:119). */
+int segsde_dropout_fwd(const segsde_nhwc_t* x, const segsde_nhwc_t* y, float p, uint64_t seed,
+                       uint64_t offset, const float* mask_in, uint8_t* mask_out, int channelwise,
+                       void* stream);
+int segsde_dropout_bwd(const segsde_nhwc_t* dy, const uint8_t* mask, float p, int channelwise,
+                       const segsde_nhwc_t* dx, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Pose head (models/pose_decoder.py:53-58, models/monodepth_layers.py:30-105)
+ * ------------------------------------------------------------------------------------------- */
+/* vec: [B,6] = (axisangle xyz, translation xyz) -> M: [B,16] row-major 4x4; invert as reference.
+ * jac (may be NULL): [B,12,6] d M[:3,:4] / d vec, consumed by the backward entry. */
+int segsde_pose_matrix_fwd(const float* vec, int b, int invert, float* M, float* jac, void* stream);
+int segsde_pose_matrix_bwd(const float* jac, const float* dM, int b, float* dvec, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Monodepth photometric loss (loss/monodepth_loss.py:64-192, models/monodepth_layers.py:18-27,
+ * 145-199, 224-254): bilinear disparity upsampling, disp->depth, backproject, project,
+ * grid_sample(border, align_corners=True), SSIM(3x3, reflect)+L1, identity auto-mask with
+ * tie-break noise, per-pixel min, mean — one fused kernel per scale; optional unit gradients
+ * w.r.t. the scale's disparity map and the two pose matrices in the same pass.
+ * ------------------------------------------------------------------------------------------- */
+#define SEGSDE_REPROJ_NO_SSIM 1
+#define SEGSDE_REPROJ_AVG 2
+#define SEGSDE_REPROJ_NO_AUTOMASK 4
+
+typedef struct {
+  const float* tgt;       /* [B,3,H,W] ("color",0,0) */
+  const float* src[2];    /* [B,3,H,W] ("color",f,0), f = frame_ids[1:] */
+  const float* disp;      /* [B,1,hs,ws] sigmoid disparity of this scale */
+  const float* K;         /* [B,4,4] ("K",0) */
+  const float* inv_K;     /* [B,4,4] ("inv_K",0) */
+  const float* T[2];      /* [B,4,4] cam_T_cam per source frame */
+  const float* noise;     /* [B,Fi,H,W] tie-break noise already scaled by 1e-5, or NULL = Philox */
+  uint64_t seed, offset;  /* Philox stream when noise == NULL */
+  int32_t B, H, W, hs, ws, F;
+  float min_depth, max_depth;
+  int32_t flags;          /* SEGSDE_REPROJ_* */
+  /* outputs */
+  float* loss_partial;    /* [segsde_reproj_num_partials] per-block sums of min-loss */
+  float* ident_sel;       /* [B,H,W] 1.0 where a reprojection candidate won, or NULL */
+  float* gdisp;           /* [B,1,hs,ws] d(mean min-loss)/d disp, accumulated (zero-filled), or NULL */
+  float* gT_partial;      /* [F][B][tiles][12] per-block d/dP partials (only with gdisp) */
+} segsde_reproj_args_t;
+
+int segsde_reproj_num_partials(int B, int H, int W);  /* = B * tiles */
+int segsde_reproj_tiles(int H, int W);
+int segsde_reproj_fused(const segsde_reproj_args_t* a, void* stream);
+/* loss = sum(partials)/(B*H*W); gT[f][b] (4x4) = K[:3,:]^T * sum_tiles gP. Deterministic order. */
+int segsde_reproj_finalize(const float* loss_partial, int n_partial, int64_t count, float* loss_out,
+                           const float* gT_partial, const float* K, int B, int tiles, int F,
+                           float* gT, void* stream);
+/* Optional materialisation of the reference's side outputs (monodepth_loss.py:78-98):
+ * depth [B,1,H,W], sample [B,H,W,2], colour [B,3,H,W] for one source frame. Any may be NULL. */
+int segsde_reproj_materialize(const float* src, const float* disp, const float* K,
+                              const float* inv_K, const float* T, int B, int H, int W, int hs,
+                              int ws, float min_depth, float max_depth, float* depth,
+                              float* sample, float* color, void* stream);
+/* generate_depth_test_pred (monodepth_loss.py:54-62): upsample + disp_to_depth. */
+int segsde_disp_to_depth_up(const float* disp, int B, int hs, int ws, int H, int W, float min_depth,
+                            float max_depth, float* depth, void* stream);
+
+/* Edge-aware smoothness (monodepth_layers.py:208-221 with the mean normalisation of
+ * monodepth_loss.py:182-184). Two launches: (1) per-sample disparity sums, (2) loss + gradient. */
+int segsde_smooth_mean(const float* disp, int B, int h, int w, float* mean_out /*[B]*/, void* stream);
+/* acc: [2 + B] fp32 zero-filled: acc[0]=mean_x term, acc[1]=mean_y term, acc[2+b]=sum_i ghat_i d_i.
+ * ghat (may be NULL): [B,h,w] gradient w.r.t. the normalised disparity. */
+int segsde_smooth_fused(const float* disp, const float* img, const float* mean, int B, int h, int w,
+                        float* acc, float* ghat, void* stream);
+/* gdisp += wgt * (ghat/(m+eps) - dot_b/((m+eps)^2 hw)) ; dot from acc. */
+int segsde_smooth_grad_finalize(const float* ghat, const float* mean, const float* acc, int B, int h,
+                                int w, float wgt, float* gdisp, void* stream);
+
+/* acc[0], acc[1] of segsde_smooth_fused are already divided by their element counts, so
+ * out[s] = reproj[s] + smooth_w_host[s]*(sacc[s*stride]+sacc[s*stride+1]); out[S] = mean_s out[s]
+ * (monodepth_loss.py:186-191). smooth_w_host: S HOST floats (disparity_smoothness / 2^s). */
+int segsde_mono_combine(const float* reproj, const float* sacc, int S, int sacc_stride,
+                        const float* smooth_w_host, float* out, void* stream);
+/* y (+)= (ca*a[0] + cb*b[0]) * x, a/b device scalars (upstream gradients; either may be NULL). */
+int segsde_scale_by_dev(const float* x, const float* a, float ca, const float* b, float cb, float* y,
+                        int accumulate, int64_t n, void* stream);
+
+/* y[i] = a * x[i] (+ y[i] if accumulate) — used to scale stored unit gradients. */
+int segsde_axpby(const float* x, float a, float* y, int accumulate, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Segmentation cross-entropy (loss/loss.py:17-37): ignore_index 250, mean over valid pixels,
+ * optional per-pixel weights (mean over all pixels).  logits: NHWC view; target int64 [N,H,W].
+ * acc: [2] fp32 zero-filled -> acc[0] = sum of (weighted) NLL, acc[1] = number of valid pixels.
+ * ------------------------------------------------------------------------------------------- */
+int segsde_ce_fwd(const segsde_nhwc_t* logits, const int64_t* target, const float* pixel_w,
+                  int ignore_index, float* acc, void* stream);
+/* dlogits = gscale_dev[0] * (softmax - onehot) * w ; gscale is a device scalar so that no host
+ * sync is needed to divide by the valid count. */
+int segsde_ce_bwd(const segsde_nhwc_t* logits, const int64_t* target, const float* pixel_w,
+                  int ignore_index, const float* gscale_dev, const segsde_nhwc_t* dlogits,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEGSDE_B200_H */
