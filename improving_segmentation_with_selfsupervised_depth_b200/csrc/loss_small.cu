@@ -138,6 +138,13 @@ __global__ void mono_combine_kernel(const float* __restrict__ reproj, const floa
   }
 }
 
+__global__ void ratio_kernel(const float* __restrict__ acc, float const_den, float* __restrict__ out,
+                             float* __restrict__ inv) {
+  const float den = const_den > 0.f ? const_den : acc[1];
+  out[0] = acc[0] / den;     // 0/0 -> NaN exactly like F.cross_entropy on an all-ignored batch
+  inv[0] = 1.f / den; inv[1] = 0.f;
+}
+
 // ---- cross entropy ----------------------------------------------------------------------------
 // One thread per pixel; the C logits of a pixel are contiguous (NHWC view), C is small (19).
 template <bool BWD>
@@ -231,6 +238,12 @@ extern "C" int segsde_mono_combine(const float* reproj, const float* sacc, int S
   CombineW w;
   for (int s = 0; s < 8; ++s) w.w[s] = s < S ? smooth_w_host[s] : 0.f;
   mono_combine_kernel<<<1, 32, 0, as_stream(stream)>>>(reproj, sacc, S, sacc_stride, w, out);
+  return launched();
+}
+
+extern "C" int segsde_ratio(const float* acc, float const_den, float* out, float* inv, void* stream) {
+  if (!acc || !out || !inv) return SEGSDE_E_ARG;
+  ratio_kernel<<<1, 1, 0, as_stream(stream)>>>(acc, const_den, out, inv);
   return launched();
 }
 

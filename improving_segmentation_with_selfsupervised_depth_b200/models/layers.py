@@ -1,0 +1,78 @@
+"""nn.Module shells around the sm_100a kernels.  They subclass the torch modules the reference uses
+(so `isinstance(m, nn.BatchNorm2d)` checks such as train.py:433-440 keep working and the
+state_dict keys / OIHW shapes are identical) but never call torch compute ops."""
+import torch
+from torch import nn
+
+from .. import _cabi as A
+from .. import ops
+
+
+class Conv2d(nn.Conv2d):
+    """nn.Conv2d whose weight lives in channels_last memory (= the kernels' OHWI) and whose forward
+    is `ops.conv2d`.  Extra forward arguments expose the fusions of the decoder."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        if self.groups != 1 or self.padding_mode != "zeros":
+            raise NotImplementedError("segsde_b200 Conv2d: groups=1 and zero padding_mode only")
+        assert self.stride[0] == self.stride[1] and self.dilation[0] == self.dilation[1]
+        assert self.padding[0] == self.padding[1]
+        with torch.no_grad():
+            self.weight.data = self.weight.data.contiguous(memory_format=torch.channels_last)
+
+    def forward(self, x, x2=None, up1=False, act=A.ACT_NONE, pad=None, pad_mode=A.PAD_ZERO, nchw_norm_in=False):
+        return ops.conv2d(x, self.weight, self.bias, x2=x2, stride=self.stride[0],
+                          pad=self.padding[0] if pad is None else pad, dil=self.dilation[0], pad_mode=pad_mode,
+                          up1=up1, act=act, nchw_norm_in=nchw_norm_in)
+
+
+class BatchNorm2d(nn.BatchNorm2d):
+    """nn.BatchNorm2d on the fused kernels: y = act(bn(x) [+ residual])."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self._pending_batches = 0     # num_batches_tracked is flushed lazily (no per-step tiny kernel)
+
+    def forward(self, x, residual=None, act=A.ACT_NONE):
+        use_batch_stats = self.training or not self.track_running_stats
+        update = self.training and self.track_running_stats
+        momentum = self.momentum
+        if update:
+            self._pending_batches += 1
+            if momentum is None:      # cumulative moving average
+                momentum = 1.0 / float(int(self.num_batches_tracked) + self._pending_batches)
+        if use_batch_stats:           # running buffers are only passed when they must be updated
+            rm, rv = (self.running_mean, self.running_var) if update else (None, None)
+        else:
+            rm, rv = self.running_mean, self.running_var
+        return ops.batch_norm(x, self.weight, self.bias, rm, rv, use_batch_stats, momentum or 0.0, self.eps,
+                              residual=residual, act=act)
+
+    def _flush(self):
+        if self._pending_batches and self.num_batches_tracked is not None:
+            self.num_batches_tracked += self._pending_batches
+        self._pending_batches = 0
+
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        self._flush()
+        super()._save_to_state_dict(destination, prefix, keep_vars)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._pending_batches = 0
+        super()._load_from_state_dict(*args, **kwargs)
+
+
+class Dropout(nn.Dropout):
+    """nn.Dropout on the Philox dropout kernel; `replay_mask` (NCHW 0/1 tensor) pins the mask in tests."""
+    replay_mask = None
+
+    def forward(self, x):
+        return ops.dropout(x, self.p, self.training, channelwise=False, replay_mask=self.replay_mask)
+
+
+class Dropout2d(nn.Dropout2d):
+    replay_mask = None
+
+    def forward(self, x):
+        return ops.dropout(x, self.p, self.training, channelwise=True, replay_mask=self.replay_mask)

@@ -1,0 +1,101 @@
+"""ResNet-{18,34,50,101,152} trunks with torchvision-compatible attribute names / state_dict keys
+(conv1, bn1, relu, maxpool, layer1..4.{i}.{conv,bn}{1..3}, downsample.{0,1}, avgpool, fc), built
+from the kernel-backed layers.  Restates what the reference obtains from `torchvision.models.resnet*`
+(models/resnet_encoder.py:73-85): v1.5 bottleneck (stride on the 3x3) and
+`replace_stride_with_dilation` exactly as torchvision's `_make_layer`."""
+from torch import nn
+
+from .. import _cabi as A
+from .layers import BatchNorm2d, Conv2d
+
+
+class BasicBlock(nn.Module):
+    expansion = 1
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None, dilation=1):
+        super().__init__()
+        if dilation > 1:
+            raise NotImplementedError("Dilation > 1 not supported in BasicBlock")
+        self.conv1 = Conv2d(inplanes, planes, 3, stride, 1, bias=False)
+        self.bn1 = BatchNorm2d(planes)
+        self.relu = nn.ReLU(inplace=True)
+        self.conv2 = Conv2d(planes, planes, 3, 1, 1, bias=False)
+        self.bn2 = BatchNorm2d(planes)
+        self.downsample = downsample
+        self.stride = stride
+
+    def forward(self, x):
+        identity = x
+        out = self.bn1(self.conv1(x), act=A.ACT_RELU)
+        if self.downsample is not None:
+            identity = self.downsample[1](self.downsample[0](x))
+        return self.bn2(self.conv2(out), residual=identity, act=A.ACT_RELU)
+
+
+class Bottleneck(nn.Module):
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None, dilation=1):
+        super().__init__()
+        self.conv1 = Conv2d(inplanes, planes, 1, bias=False)
+        self.bn1 = BatchNorm2d(planes)
+        self.conv2 = Conv2d(planes, planes, 3, stride, dilation, dilation=dilation, bias=False)
+        self.bn2 = BatchNorm2d(planes)
+        self.conv3 = Conv2d(planes, planes * 4, 1, bias=False)
+        self.bn3 = BatchNorm2d(planes * 4)
+        self.relu = nn.ReLU(inplace=True)
+        self.downsample = downsample
+        self.stride = stride
+
+    def forward(self, x):
+        identity = x
+        out = self.bn1(self.conv1(x), act=A.ACT_RELU)
+        out = self.bn2(self.conv2(out), act=A.ACT_RELU)
+        if self.downsample is not None:
+            identity = self.downsample[1](self.downsample[0](x))
+        return self.bn3(self.conv3(out), residual=identity, act=A.ACT_RELU)
+
+
+CONFIGS = {18: (BasicBlock, [2, 2, 2, 2]), 34: (BasicBlock, [3, 4, 6, 3]), 50: (Bottleneck, [3, 4, 6, 3]),
+           101: (Bottleneck, [3, 4, 23, 3]), 152: (Bottleneck, [3, 8, 36, 3])}
+
+
+class ResNet(nn.Module):
+    def __init__(self, num_layers, in_channels=3, replace_stride_with_dilation=None, num_classes=1000):
+        super().__init__()
+        block, layers = CONFIGS[num_layers]
+        if replace_stride_with_dilation is None:
+            replace_stride_with_dilation = [False, False, False]
+        if len(replace_stride_with_dilation) != 3:
+            raise ValueError("replace_stride_with_dilation should be None or a 3-element tuple")
+        self.inplanes, self.dilation = 64, 1
+        self.conv1 = Conv2d(in_channels, 64, 7, 2, 3, bias=False)
+        self.bn1 = BatchNorm2d(64)
+        self.relu = nn.ReLU(inplace=True)
+        self.maxpool = nn.MaxPool2d(3, 2, 1)
+        self.layer1 = self._make_layer(block, 64, layers[0])
+        self.layer2 = self._make_layer(block, 128, layers[1], 2, replace_stride_with_dilation[0])
+        self.layer3 = self._make_layer(block, 256, layers[2], 2, replace_stride_with_dilation[1])
+        self.layer4 = self._make_layer(block, 512, layers[3], 2, replace_stride_with_dilation[2])
+        self.avgpool = nn.AdaptiveAvgPool2d((1, 1))
+        self.fc = nn.Linear(512 * block.expansion, num_classes)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+
+    def _make_layer(self, block, planes, blocks, stride=1, dilate=False):
+        downsample, previous_dilation = None, self.dilation
+        if dilate:
+            self.dilation *= stride
+            stride = 1
+        if stride != 1 or self.inplanes != planes * block.expansion:
+            downsample = nn.Sequential(Conv2d(self.inplanes, planes * block.expansion, 1, stride, bias=False),
+                                       BatchNorm2d(planes * block.expansion))
+        layers = [block(self.inplanes, planes, stride, downsample, previous_dilation)]
+        self.inplanes = planes * block.expansion
+        for _ in range(1, blocks):
+            layers.append(block(self.inplanes, planes, dilation=self.dilation))
+        return nn.Sequential(*layers)

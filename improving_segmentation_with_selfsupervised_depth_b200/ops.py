@@ -1,0 +1,539 @@
+"""torch.autograd glue over the C-ABI kernels (include/segsde_b200.h).
+
+Tensors cross this layer with the reference's NCHW *shape* but channels-last *memory* (channel
+stride 1): the kernels see strided NHWC views, user code sees the shapes it expects.  No op here
+computes anything with torch: torch only owns memory (caching allocator), streams and the autograd
+graph.  Every op raises if it is handed a CPU tensor — there is no fallback.
+"""
+import ctypes as C
+
+import torch
+
+from . import _cabi as A
+
+# route eligible convolutions to the tcgen05 tensor-core kernels (set False to force the generic path)
+USE_TC = True
+
+
+# -------------------------------------------------------------------------------------------------
+# layout helpers
+# -------------------------------------------------------------------------------------------------
+def cl_empty(n, c, h, w, device, zero=False):
+    f = torch.zeros if zero else torch.empty
+    return f((n, h, w, c), device=device, dtype=torch.float32).permute(0, 3, 1, 2)
+
+
+def is_cl(x):
+    return x.dim() == 4 and (x.shape[1] == 1 or x.stride(1) == 1) and x.dtype == torch.float32
+
+
+def as_cl(x):
+    """Returns x with channel stride 1 (converting with the layout kernel when necessary)."""
+    A.require_cuda(x)
+    if x.dtype != torch.float32:
+        x = x.float()
+    if is_cl(x) and all(s >= 0 for s in x.stride()):
+        return x
+    n, c, h, w = x.shape
+    y = cl_empty(n, c, h, w, x.device)
+    A.call("segsde_nchw_to_nhwc", A.ptr(x), C.c_int64(x.stride(0)), C.c_int64(x.stride(1)),
+           C.c_int64(x.stride(2)), C.c_int64(x.stride(3)), C.byref(view(y)), A.stream_ptr())
+    return y
+
+
+def view(x, null=False):
+    """NHWC view struct of an NCHW-shaped tensor with channel stride 1."""
+    n, c, h, w = x.shape
+    v = A.NHWC()
+    v.ptr = None if null else x.data_ptr()
+    v.n, v.h, v.w, v.c = n, h, w, c
+    v.sn, v.sh, v.sw = x.stride(0), x.stride(2), x.stride(3)
+    return v
+
+
+def shape_view(n, c, h, w):
+    v = A.NHWC()
+    v.ptr = None
+    v.n, v.h, v.w, v.c = n, h, w, c
+    v.sn, v.sh, v.sw = h * w * c, w * c, c
+    return v
+
+
+def _ref(v):
+    return C.byref(v) if v is not None else None
+
+
+def ohwi(w):
+    """Weight as a dense [O][kh][kw][I] block: an OIHW tensor in channels_last memory."""
+    if w.permute(0, 2, 3, 1).is_contiguous():
+        return w
+    return w.contiguous(memory_format=torch.channels_last)
+
+
+# -------------------------------------------------------------------------------------------------
+# convolution
+# -------------------------------------------------------------------------------------------------
+def _desc(kh, kw, stride, pad, dil, pad_mode, up1, act, nchw):
+    d = A.ConvDesc()
+    d.kh, d.kw, d.stride, d.pad, d.dil = kh, kw, stride, pad, dil
+    d.pad_mode, d.up1, d.act, d.nchw_norm_in = pad_mode, int(up1), act, int(nchw)
+    return d
+
+
+def _conv_out_hw(hc, wc, kh, kw, stride, pad, dil):
+    return ((hc + 2 * pad - dil * (kh - 1) - 1) // stride + 1,
+            (wc + 2 * pad - dil * (kw - 1) - 1) // stride + 1)
+
+
+class _Conv2dFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x1, x2, weight, bias, stride, pad, dil, pad_mode, up1, act, nchw):
+        A.require_cuda(x1, weight)
+        if nchw:
+            x1 = x1.contiguous()
+            x2 = x2.contiguous() if x2 is not None else None
+        else:
+            x1 = as_cl(x1)
+            x2 = as_cl(x2) if x2 is not None else None
+        w = ohwi(weight.detach())
+        cout, _, kh, kw = w.shape
+        n, _, h1, w1 = x1.shape
+        hc, wc = (h1 * 2, w1 * 2) if up1 else (h1, w1)
+        ho, wo = _conv_out_hw(hc, wc, kh, kw, stride, pad, dil)
+        y = cl_empty(n, cout, ho, wo, x1.device)
+        d = _desc(kh, kw, stride, pad, dil, pad_mode, up1, act, nchw)
+        v1, v2, vy = view(x1), (view(x2) if x2 is not None else None), view(y)
+        if nchw:   # planar image: only the shape fields are meaningful
+            v1.sn = v1.sh = v1.sw = 0
+        b = bias.detach() if bias is not None else None
+        st = A.stream_ptr()
+        done = False
+        if USE_TC and not nchw:
+            done = A.try_call("segsde_conv2d_fwd_tc", C.byref(v1), _ref(v2), A.ptr(w), A.ptr(b), C.byref(vy),
+                              C.byref(d), st)
+        if not done:
+            A.call("segsde_conv2d_fwd", C.byref(v1), _ref(v2), A.ptr(w), A.ptr(b), C.byref(vy), C.byref(d), st)
+        ctx.save_for_backward(x1, x2, w, y if act != A.ACT_NONE else None)
+        ctx.cfg = (stride, pad, dil, pad_mode, up1, act, nchw, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x1, x2, w, y = ctx.saved_tensors
+        stride, pad, dil, pad_mode, up1, act, nchw, has_bias = ctx.cfg
+        cout, _, kh, kw = w.shape
+        st = A.stream_ptr()
+        dy = as_cl(dy)
+        if act != A.ACT_NONE:
+            dz = cl_empty(*dy.shape, dy.device)
+            A.call("segsde_act_bwd", C.byref(view(y)), C.byref(view(dy)), C.byref(view(dz)), C.c_int(act), st)
+        else:
+            dz = dy
+        d = _desc(kh, kw, stride, pad, dil, pad_mode, up1, A.ACT_NONE, nchw)
+        vdz = view(dz)
+        need1, need2, needw, needb = ctx.needs_input_grad[0], ctx.needs_input_grad[1], \
+            ctx.needs_input_grad[2], ctx.needs_input_grad[3]
+        dx1 = dx2 = dw = db = None
+        if (need1 or need2) and not nchw:
+            folded = pad_mode == A.PAD_REFLECT or up1
+            if need1:
+                dx1 = cl_empty(*x1.shape, x1.device, zero=folded)
+            if need2 and x2 is not None:
+                dx2 = cl_empty(*x2.shape, x2.device, zero=folded)
+            g1 = view(dx1) if dx1 is not None else view(x1, null=True)
+            g2 = (view(dx2) if dx2 is not None else view(x2, null=True)) if x2 is not None else None
+            done = False
+            if USE_TC:
+                done = A.try_call("segsde_conv2d_dgrad_tc", C.byref(vdz), A.ptr(w), C.byref(g1), _ref(g2),
+                                  C.byref(d), st)
+            if not done:
+                A.call("segsde_conv2d_dgrad", C.byref(vdz), A.ptr(w), C.byref(g1), _ref(g2), C.byref(d), st)
+        if needw or (needb and has_bias):
+            dw = torch.zeros_like(w)
+            db = torch.zeros(cout, device=w.device, dtype=torch.float32) if has_bias else None
+            v1, v2 = view(x1), (view(x2) if x2 is not None else None)
+            if nchw:
+                v1.sn = v1.sh = v1.sw = 0
+            done = False
+            if USE_TC and not nchw:
+                done = A.try_call("segsde_conv2d_wgrad_tc", C.byref(v1), _ref(v2), C.byref(vdz), A.ptr(dw),
+                                  A.ptr(db), C.byref(d), st)
+            if not done:
+                A.call("segsde_conv2d_wgrad", C.byref(v1), _ref(v2), C.byref(vdz), A.ptr(dw), A.ptr(db),
+                       C.byref(d), st)
+        return dx1, dx2, dw, db, None, None, None, None, None, None, None
+
+
+def conv2d(x1, weight, bias=None, x2=None, stride=1, pad=0, dil=1, pad_mode=A.PAD_ZERO, up1=False,
+           act=A.ACT_NONE, nchw_norm_in=False):
+    """y = act(conv(cat(up?(x1), x2)) + bias) — see segsde_conv2d_fwd."""
+    return _Conv2dFn.apply(x1, x2, weight, bias, stride, pad, dil, pad_mode, up1, act, nchw_norm_in)
+
+
+# -------------------------------------------------------------------------------------------------
+# batch norm (+ residual + ReLU)
+# -------------------------------------------------------------------------------------------------
+class _BatchNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, running_mean, running_var, training, momentum, eps, act):
+        x = as_cl(x)
+        residual = as_cl(residual) if residual is not None else None
+        n, c, h, w = x.shape
+        dev, st = x.device, A.stream_ptr()
+        mean = torch.empty(c, device=dev, dtype=torch.float32)
+        invstd = torch.empty(c, device=dev, dtype=torch.float32)
+        if training:
+            sums = torch.zeros(2 * c, device=dev, dtype=torch.float64)
+            A.call("segsde_bn_stats", C.byref(view(x)), A.ptr(sums), st)
+            A.call("segsde_bn_finalize", A.ptr(sums), C.c_int(c), C.c_int64(n * h * w), C.c_float(eps),
+                   C.c_float(momentum), A.ptr(mean), A.ptr(invstd), A.ptr(running_mean), A.ptr(running_var), st)
+        else:
+            A.call("segsde_bn_eval_prepare", A.ptr(running_mean), A.ptr(running_var), C.c_int(c), C.c_float(eps),
+                   A.ptr(mean), A.ptr(invstd), st)
+        y = cl_empty(n, c, h, w, dev)
+        gw = weight.detach() if weight is not None else None
+        gb = bias.detach() if bias is not None else None
+        A.call("segsde_bn_apply", C.byref(view(x)), A.ptr(mean), A.ptr(invstd), A.ptr(gw), A.ptr(gb),
+               _ref(view(residual)) if residual is not None else None, C.byref(view(y)), C.c_int(act), st)
+        ctx.save_for_backward(x, y if act == A.ACT_RELU else None, mean, invstd, gw)
+        ctx.cfg = (training, act, residual is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, mean, invstd, gw = ctx.saved_tensors
+        training, act, has_res = ctx.cfg
+        dy = as_cl(dy)
+        n, c, h, w = x.shape
+        dev, st = x.device, A.stream_ptr()
+        red = torch.zeros(2 * c, device=dev, dtype=torch.float64)
+        vy = view(y) if y is not None else None
+        A.call("segsde_bn_bwd_reduce", C.byref(view(x)), _ref(vy), C.byref(view(dy)), A.ptr(mean), A.ptr(invstd),
+               C.c_int(act), A.ptr(red), st)
+        need_x, need_w, need_b, need_r = ctx.needs_input_grad[:4]
+        dx = cl_empty(n, c, h, w, dev) if need_x else None
+        dres = cl_empty(n, c, h, w, dev) if (has_res and need_r) else None
+        dgamma = torch.zeros(c, device=dev, dtype=torch.float32) if need_w else None
+        dbeta = torch.zeros(c, device=dev, dtype=torch.float32) if need_b else None
+        A.call("segsde_bn_bwd_apply", C.byref(view(x)), _ref(vy), C.byref(view(dy)), A.ptr(mean), A.ptr(invstd),
+               A.ptr(gw), C.c_int(act), C.c_int(1 if training else 0), A.ptr(red), C.c_int64(n * h * w),
+               _ref(view(dx)) if dx is not None else None, _ref(view(dres)) if dres is not None else None,
+               A.ptr(dgamma), A.ptr(dbeta), st)
+        return dx, dgamma, dbeta, dres, None, None, None, None, None, None
+
+
+def batch_norm(x, weight, bias, running_mean, running_var, training, momentum=0.1, eps=1e-5, residual=None,
+               act=A.ACT_NONE):
+    """training=True: batch statistics (running buffers, when given, are updated in place);
+    training=False: normalise with the running buffers."""
+    return _BatchNormFn.apply(x, weight, bias, residual, running_mean, running_var, bool(training),
+                              0.0 if momentum is None else momentum, eps, act)
+
+
+# -------------------------------------------------------------------------------------------------
+# pooling / resampling / elementwise
+# -------------------------------------------------------------------------------------------------
+class _MaxPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = as_cl(x)
+        n, c, h, w = x.shape
+        ho, wo = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
+        y = cl_empty(n, c, ho, wo, x.device)
+        idx = torch.empty(n * ho * wo * c, device=x.device, dtype=torch.uint8)
+        A.call("segsde_maxpool3x3s2_fwd", C.byref(view(x)), C.byref(view(y)), A.ptr(idx), A.stream_ptr())
+        ctx.save_for_backward(idx)
+        ctx.in_shape = x.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (idx,) = ctx.saved_tensors
+        dy = as_cl(dy)
+        dx = cl_empty(*ctx.in_shape, dy.device)
+        A.call("segsde_maxpool3x3s2_bwd", C.byref(view(dy)), A.ptr(idx), C.byref(view(dx)), A.stream_ptr())
+        return dx
+
+
+def maxpool3x3s2(x):
+    return _MaxPoolFn.apply(x)
+
+
+class _SpatialMeanFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, scale):
+        x = as_cl(x)
+        n, c, h, w = x.shape
+        y = cl_empty(n, c, 1, 1, x.device)
+        A.call("segsde_spatial_mean_fwd", C.byref(view(x)), C.byref(view(y)), C.c_float(scale), A.stream_ptr())
+        ctx.in_shape, ctx.scale = x.shape, scale
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = as_cl(dy)
+        dx = cl_empty(*ctx.in_shape, dy.device)
+        A.call("segsde_spatial_mean_bwd", C.byref(view(dy)), C.byref(view(dx)), C.c_float(ctx.scale), A.stream_ptr())
+        return dx, None
+
+
+def spatial_mean(x, scale=1.0):
+    """[N,C,H,W] -> [N,C,1,1] = scale * mean over H,W."""
+    return _SpatialMeanFn.apply(x, scale)
+
+
+class _BroadcastFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, h, w):
+        x = as_cl(x)
+        n, c = x.shape[:2]
+        y = cl_empty(n, c, h, w, x.device)
+        A.call("segsde_broadcast_hw_fwd", C.byref(view(x)), C.byref(view(y)), A.stream_ptr())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = as_cl(dy)
+        n, c = dy.shape[:2]
+        dx = cl_empty(n, c, 1, 1, dy.device)
+        A.call("segsde_broadcast_hw_bwd", C.byref(view(dy)), C.byref(view(dx)), A.stream_ptr())
+        return dx, None, None
+
+
+def broadcast_hw(x, h, w):
+    """Bilinear resize from 1x1 (ASPPPooling) == broadcast."""
+    return _BroadcastFn.apply(x, h, w)
+
+
+class _CatFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, *xs):
+        xs = [as_cl(x) for x in xs]
+        n, _, h, w = xs[0].shape
+        cs = [x.shape[1] for x in xs]
+        y = cl_empty(n, sum(cs), h, w, xs[0].device)
+        st, c0 = A.stream_ptr(), 0
+        for x, c in zip(xs, cs):
+            A.call("segsde_copy_nhwc", C.byref(view(x)), C.byref(view(y[:, c0:c0 + c])), st)
+            c0 += c
+        ctx.cs = cs
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        out, c0 = [], 0
+        for c in ctx.cs:
+            out.append(dy[:, c0:c0 + c])
+            c0 += c
+        return tuple(out)
+
+
+def cat_channels(xs):
+    return _CatFn.apply(*xs)
+
+
+class _AddFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = as_cl(a), as_cl(b)
+        y = cl_empty(*a.shape, a.device)
+        A.call("segsde_add", C.byref(view(a)), C.byref(view(b)), C.byref(view(y)), A.stream_ptr())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy, dy
+
+
+def add(a, b):
+    return _AddFn.apply(a, b)
+
+
+class _GateFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, f, a):
+        f, a = as_cl(f), as_cl(a)
+        y = cl_empty(*f.shape, f.device)
+        A.call("segsde_gate_fwd", C.byref(view(f)), C.byref(view(a)), C.byref(view(y)), A.stream_ptr())
+        ctx.save_for_backward(f, a)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        f, a = ctx.saved_tensors
+        dy = as_cl(dy)
+        df, da = cl_empty(*f.shape, f.device), cl_empty(*f.shape, f.device)
+        A.call("segsde_gate_bwd", C.byref(view(f)), C.byref(view(a)), C.byref(view(dy)), C.byref(view(df)),
+               C.byref(view(da)), A.stream_ptr())
+        return df, da
+
+
+def gate(features, attention):
+    """features * sigmoid(attention) (SelfAttention, model_parts.py:43-45)."""
+    return _GateFn.apply(features, attention)
+
+
+class _BilinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, h, w, align):
+        x = as_cl(x)
+        n, c = x.shape[:2]
+        y = cl_empty(n, c, h, w, x.device)
+        A.call("segsde_bilinear_fwd", C.byref(view(x)), C.byref(view(y)), C.c_int(int(align)), A.stream_ptr())
+        ctx.in_shape, ctx.align = x.shape, align
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = as_cl(dy)
+        dx = cl_empty(*ctx.in_shape, dy.device, zero=True)
+        A.call("segsde_bilinear_bwd", C.byref(view(dy)), C.byref(view(dx)), C.c_int(int(ctx.align)), A.stream_ptr())
+        return dx, None, None, None
+
+
+def bilinear(x, size, align_corners=False):
+    return _BilinearFn.apply(x, int(size[0]), int(size[1]), bool(align_corners))
+
+
+class _ActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, act):
+        x = as_cl(x)
+        y = cl_empty(*x.shape, x.device)
+        A.call("segsde_act_fwd", C.byref(view(x)), C.byref(view(y)), C.c_int(act), A.stream_ptr())
+        ctx.save_for_backward(y)
+        ctx.act = act
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        dy = as_cl(dy)
+        dz = cl_empty(*dy.shape, dy.device)
+        A.call("segsde_act_bwd", C.byref(view(y)), C.byref(view(dy)), C.byref(view(dz)), C.c_int(ctx.act), A.stream_ptr())
+        return dz, None
+
+
+def activation(x, act):
+    return _ActFn.apply(x, act)
+
+
+_DROPOUT_STEP = [0]
+
+
+class _DropoutFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p, channelwise, seed, replay_mask):
+        x = as_cl(x)
+        n, c, h, w = x.shape
+        y = cl_empty(n, c, h, w, x.device)
+        mask = torch.empty(n * c if channelwise else n * c * h * w, device=x.device, dtype=torch.uint8)
+        _DROPOUT_STEP[0] += 1
+        rm = replay_mask.to(x.device, torch.float32).contiguous() if replay_mask is not None else None
+        A.call("segsde_dropout_fwd", C.byref(view(x)), C.byref(view(y)), C.c_float(p), C.c_uint64(seed),
+               C.c_uint64(_DROPOUT_STEP[0]), A.ptr(rm), A.ptr(mask), C.c_int(int(channelwise)), A.stream_ptr())
+        ctx.save_for_backward(mask)
+        ctx.cfg = (p, channelwise)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (mask,) = ctx.saved_tensors
+        p, channelwise = ctx.cfg
+        dy = as_cl(dy)
+        dx = cl_empty(*dy.shape, dy.device)
+        A.call("segsde_dropout_bwd", C.byref(view(dy)), A.ptr(mask), C.c_float(p), C.c_int(int(channelwise)),
+               C.byref(view(dx)), A.stream_ptr())
+        return dx, None, None, None, None
+
+
+def dropout(x, p, training, channelwise=False, seed=0xD20B007, replay_mask=None):
+    if not training or p <= 0.0:
+        return x
+    return _DropoutFn.apply(x, float(p), channelwise, seed, replay_mask)
+
+
+# -------------------------------------------------------------------------------------------------
+# pose geometry
+# -------------------------------------------------------------------------------------------------
+class _PoseMatrixFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, vec, invert):
+        A.require_cuda(vec)
+        v = vec.detach().reshape(-1, 6).contiguous().float()
+        b = v.shape[0]
+        M = torch.empty(b, 4, 4, device=v.device, dtype=torch.float32)
+        jac = torch.empty(b, 12, 6, device=v.device, dtype=torch.float32)
+        A.call("segsde_pose_matrix_fwd", A.ptr(v), C.c_int(b), C.c_int(int(invert)), A.ptr(M), A.ptr(jac), A.stream_ptr())
+        ctx.save_for_backward(jac)
+        ctx.in_shape = vec.shape
+        return M
+
+    @staticmethod
+    def backward(ctx, dM):
+        (jac,) = ctx.saved_tensors
+        b = jac.shape[0]
+        dM = dM.contiguous().float()
+        dv = torch.empty(b, 6, device=dM.device, dtype=torch.float32)
+        A.call("segsde_pose_matrix_bwd", A.ptr(jac), A.ptr(dM), C.c_int(b), A.ptr(dv), A.stream_ptr())
+        return dv.view(ctx.in_shape), None
+
+
+def pose_matrix(vec6, invert):
+    """vec6: [B,6] (axis-angle, translation) -> [B,4,4] (monodepth_layers.py:30-47)."""
+    return _PoseMatrixFn.apply(vec6, invert)
+
+
+# -------------------------------------------------------------------------------------------------
+# cross entropy
+# -------------------------------------------------------------------------------------------------
+class _CrossEntropyFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, target, pixel_weights, ignore_index):
+        logits = as_cl(logits)
+        A.require_cuda(target)
+        target = target.contiguous()
+        pw = pixel_weights.detach().contiguous().float() if pixel_weights is not None else None
+        acc = torch.zeros(2, device=logits.device, dtype=torch.float32)
+        A.call("segsde_ce_fwd", C.byref(view(logits)), A.ptr(target), A.ptr(pw), C.c_int(ignore_index),
+               A.ptr(acc), A.stream_ptr())
+        ctx.save_for_backward(logits, target, pw, acc)
+        ctx.ignore_index = ignore_index
+        return acc
+
+    @staticmethod
+    def backward(ctx, gacc):
+        # gacc[0] = d loss / d (sum of NLL); the caller divides by the count through _ScalarDivFn
+        logits, target, pw, acc = ctx.saved_tensors
+        g = gacc.contiguous()
+        dl = cl_empty(*logits.shape, logits.device)
+        A.call("segsde_ce_bwd", C.byref(view(logits)), A.ptr(target), A.ptr(pw), C.c_int(ctx.ignore_index),
+               A.ptr(g), C.byref(view(dl)), A.stream_ptr())
+        return dl, None, None, None
+
+
+class _RatioFn(torch.autograd.Function):
+    """loss = acc[0] / den where den is acc[1] (valid count, mean reduction) or a host constant."""
+
+    @staticmethod
+    def forward(ctx, acc, const_den):
+        out = torch.empty((), device=acc.device, dtype=torch.float32)
+        inv = torch.empty(2, device=acc.device, dtype=torch.float32)
+        A.call("segsde_ratio", A.ptr(acc), C.c_float(const_den), A.ptr(out), A.ptr(inv), A.stream_ptr())
+        ctx.save_for_backward(inv)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (inv,) = ctx.saved_tensors
+        out = torch.zeros(2, device=inv.device, dtype=torch.float32)
+        A.call("segsde_scale_by_dev", A.ptr(inv), A.ptr(g.contiguous()), C.c_float(1.0), None, C.c_float(0.0),
+               A.ptr(out), C.c_int(0), C.c_int64(1), A.stream_ptr())
+        return out, None
+
+
+def cross_entropy(logits, target, pixel_weights=None, ignore_index=250):
+    """Mean NLL over valid pixels, or mean over all pixels of w*NLL when pixel_weights is given."""
+    acc = _CrossEntropyFn.apply(logits, target, pixel_weights, ignore_index)
+    den = 0.0 if pixel_weights is None else float(target.numel())
+    return _RatioFn.apply(acc, den)

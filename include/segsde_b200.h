@@ -93,6 +93,8 @@ int segsde_conv2d_wgrad_tc(const segsde_nhwc_t* x1, const segsde_nhwc_t* x2,
 /* 1 if this process can run the tensor-core path (driver entry point for tensor maps found). */
 int segsde_tc_available(void);
 
+/* y = act(x) as a standalone pass (ConvBlock with BatchNorm: conv -> BN -> ELU). */
+int segsde_act_fwd(const segsde_nhwc_t* x, const segsde_nhwc_t* y, int act, void* stream);
 /* dz = dy * act'(y) computed from the activation OUTPUT y (ReLU/ELU/sigmoid). In-place allowed. */
 int segsde_act_bwd(const segsde_nhwc_t* y, const segsde_nhwc_t* dy, const segsde_nhwc_t* dz, int act,
                    void* stream);
@@ -255,6 +257,18 @@ int segsde_ce_fwd(const segsde_nhwc_t* logits, const int64_t* target, const floa
 int segsde_ce_bwd(const segsde_nhwc_t* logits, const int64_t* target, const float* pixel_w,
                   int ignore_index, const float* gscale_dev, const segsde_nhwc_t* dlogits,
                   void* stream);
+
+/* Standalone layer forms (models/monodepth_layers.py:145-254), NCHW planar fp32 as in the reference. */
+int segsde_backproject(const float* depth, const float* inv_K, int B, int H, int W, float* out /*[B,4,HW]*/,
+                       void* stream);
+int segsde_project3d(const float* points /*[B,4,HW]*/, const float* K, const float* T, int B, int H, int W,
+                     float eps, float* out /*[B,H,W,2]*/, void* stream);
+int segsde_ssim_map(const float* x, const float* y, int planes, int H, int W, float* out, void* stream);
+int segsde_upsample2x_nearest(const segsde_nhwc_t* x, const segsde_nhwc_t* y, void* stream);
+
+/* out[0] = acc[0]/den, inv[0] = 1/den, inv[1] = 0 with den = const_den > 0 ? const_den : acc[1]
+ * (the "mean over valid pixels" division of F.cross_entropy without a host sync). */
+int segsde_ratio(const float* acc, float const_den, float* out, float* inv, void* stream);
 
 #ifdef __cplusplus
 }

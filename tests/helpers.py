@@ -1,0 +1,37 @@
+"""Shared test helpers (CPU oracle side + comparison utilities)."""
+import numpy as np
+import torch
+
+import segsde_oracle as O
+
+LOSS_KW = dict(min_depth=0.1, max_depth=100, test_min_depth=1e-3, test_max_depth=80, disparity_smoothness=1e-3,
+               no_ssim=False, avg_reprojection=False, disable_automasking=False)
+
+
+def rel_err(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
+
+
+def loss_case(golden):
+    """The loss-level case of tests/golden/make_golden.py: inputs, disparities, poses."""
+    B, H, W = 2, 64, 96
+    inputs = O.synthetic_inputs(B, H, W, seed=7)
+    disps = [torch.from_numpy(golden["loss_disp%d" % s]).clone() for s in range(4)]
+    Ts = {-1: torch.from_numpy(golden["loss_T-1"]).clone(), 1: torch.from_numpy(golden["loss_T1"]).clone()}
+    return B, H, W, inputs, disps, Ts
+
+
+def loss_noise(B, H, W, avg):
+    torch.manual_seed(11)
+    return [torch.randn(B, 1 if avg else 2, H, W) * 0.00001 for _ in range(4)]
+
+
+def model_cfg_from_contract(c):
+    return dict(c["cfg"])
+
+
+def unpack_mask(golden, prefix):
+    shape = tuple(int(v) for v in golden[prefix + "dropout_shape"])
+    bits = np.unpackbits(golden[prefix + "dropout_mask"])[:int(np.prod(shape))]
+    return torch.from_numpy(bits.reshape(shape).astype(np.float32))

@@ -1,0 +1,98 @@
+"""GPU: the whole drop-in network (encoder + ASPP depth decoder + pose net) and one training-step gradient
+against the committed reference outputs and the CPU oracle.  fp32 CUDA-core path: activations 2e-4, loss 2e-5,
+gradients 5e-3 relative (per-tensor norm) — batch-norm over B*H*W ~ 100 elements at the bottleneck amplifies
+summation-order noise in the gradients."""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+import torch
+
+import segsde_oracle as O
+from helpers import LOSS_KW, rel_err, unpack_mask
+
+pytestmark = pytest.mark.gpu
+
+
+def build(contracts, name, H, W, use_tc=False):
+    import improving_segmentation_with_selfsupervised_depth_b200 as P
+    from improving_segmentation_with_selfsupervised_depth_b200 import ops
+    ops.USE_TC = use_tc
+    models, _ = P.install_dropin()
+    c = contracts[name]
+    cfg = dict(c["cfg"])
+    cfg.update({"height": H, "width": W, "crop_h": H, "crop_w": W})
+    cfg["depth_args"] = dict(cfg["depth_args"], max_scale_size=[H, W])
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = models.get_model(cfg, 19)
+    sd = O.synthetic_state_dict({k: torch.empty(s) for k, s in c["state_dict"].items()}, seed=1)
+    m.load_state_dict(sd)
+    return m.cuda().train(), sd
+
+
+@pytest.mark.parametrize("name,hw", [("mono_r18", (64, 128)), ("mono_r50", (64, 96))])
+def test_model_step_vs_reference_golden(golden, contracts, name, hw):
+    from improving_segmentation_with_selfsupervised_depth_b200.loss import MonodepthLoss
+    from improving_segmentation_with_selfsupervised_depth_b200.models.layers import Dropout
+    H, W = hw
+    B = 2
+    p = "model_%s_" % name
+    model, _ = build(contracts, name, H, W)
+    for mod in model.modules():
+        if isinstance(mod, Dropout):
+            mod.replay_mask = unpack_mask(golden, p)
+    inputs = {k: v.cuda() for k, v in O.synthetic_inputs(B, H, W, seed=5).items()}
+    with contextlib.redirect_stdout(io.StringIO()):
+        out = model(inputs)
+    for s in range(4):
+        assert out[("disp", s)].shape == golden[p + "disp%d" % s].shape
+        assert rel_err(out[("disp", s)], golden[p + "disp%d" % s]) < 2e-4, s
+    for f in (-1, 1):
+        assert rel_err(out[("cam_T_cam", 0, f)], golden[p + "T%d" % f]) < 1e-4
+    ml = MonodepthLoss(num_scales=4, frame_ids=[0, -1, 1], height=H, width=W, batch_size=B, **LOSS_KW)
+    torch.manual_seed(31)
+    ml.replay_noise = [torch.randn(B, 2, H, W) * 0.00001 for _ in range(4)]
+    ml.generate_images_pred(inputs, out)
+    losses = ml.compute_losses(inputs, out)
+    vals = np.array([losses["loss/%d" % s].item() for s in range(4)] + [losses["loss"].item()])
+    np.testing.assert_allclose(vals, golden[p + "losses"], rtol=5e-5)
+    losses["loss"].backward()
+    params = dict(model.named_parameters())
+    names = [str(n) for n in golden[p + "grad_names"]]
+    norms = np.array([params[n].grad.norm().item() for n in names])
+    ref = golden[p + "grad_norms"]
+    bad = [(n, a, b) for n, a, b in zip(names, norms, ref) if abs(a - b) > 5e-3 * b + 1e-9]
+    assert not bad, bad[:5]
+    assert rel_err(params["models.encoder.encoder.conv1.weight"].grad, golden[p + "grad_enc_conv1"]) < 5e-3
+    assert rel_err(params["models.pose.net.3.weight"].grad, golden[p + "grad_pose3"]) < 5e-3
+    sd = model.state_dict()
+    assert rel_err(sd["models.encoder.encoder.bn1.running_mean"], golden[p + "bn1_running_mean"]) < 1e-5
+    assert rel_err(sd["models.encoder.encoder.bn1.running_var"], golden[p + "bn1_running_var"]) < 1e-5
+    assert int(sd["models.encoder.encoder.bn1.num_batches_tracked"]) == 1
+
+
+def test_frozen_encoder_and_eval_mode(contracts):
+    """Config-2 style freezing (freeze_backbone: only decoder+pose get gradients) and eval-mode BN."""
+    H, W, B = 64, 96, 2
+    model, sd = build(contracts, "mono_r50", H, W)
+    for q in model.models["encoder"].parameters():
+        q.requires_grad = False
+    inputs = {k: v.cuda() for k, v in O.synthetic_inputs(B, H, W, seed=6).items()}
+    with contextlib.redirect_stdout(io.StringIO()):
+        out = model(inputs)
+    (out[("disp", 0)].mean() + out[("cam_T_cam", 0, 1)].sum()).backward()
+    assert all(q.grad is None for q in model.models["encoder"].parameters())
+    assert all(q.grad is not None for q in model.models["depth"].parameters())
+    model.eval()
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        ev = model(inputs)
+    model2, _ = build(contracts, "mono_r50", H, W)
+    osd = {k: v.clone() for k, v in model.state_dict().items()}
+    cpu_sd = {k: v.cpu() for k, v in osd.items()}
+    cfg = {"num_layers": 50, "rswd": [False, False, True], "frame_ids": [0, -1, 1]}
+    cin = {k: v.cpu() for k, v in inputs.items()}
+    with torch.no_grad():
+        ref = O.model_forward(cpu_sd, cin, cfg, O.BNMode(False))
+    for s in range(4):
+        assert rel_err(ev[("disp", s)], ref[("disp", s)]) < 2e-4
