@@ -50,25 +50,23 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(View x, View y, View d
   const int c = blockIdx.x * 32 + threadIdx.x;
   const long long P = (long long)x.n * x.h * x.w;
   const long long pbeg = (long long)blockIdx.y * slab, pend = min(P, pbeg + slab);
-  float s0 = 0.f, s1 = 0.f;
   float mu = 0.f, is = 0.f;
   if (MODE == 1 && c < x.c) { mu = mean[c]; is = invstd[c]; }
+  // fp64 accumulation: var = E[x^2] - mean^2 cancels catastrophically in fp32 when var << mean^2
+  // (e.g. ASPPPooling's BatchNorm over B x 256 x 1 x 1 with similar samples); float*float is exact in double.
   double d0 = 0.0, d1 = 0.0;
-  int cnt = 0;
   if (c < x.c) {
     for (long long p = pbeg + threadIdx.y; p < pend; p += 8) {
       const int w = (int)(p % x.w); const long long q = p / x.w;
       const int h = (int)(q % x.h), n = (int)(q / x.h);
       const float xv = x.p[x.off(n, h, w) + c];
-      if (MODE == 0) { s0 += xv; s1 += xv * xv; }
+      if (MODE == 0) { d0 += (double)xv; d1 += (double)xv * (double)xv; }
       else {
         float g = dy.p[dy.off(n, h, w) + c];
         if (relu && !(y.p[y.off(n, h, w) + c] > 0.f)) g = 0.f;
-        s0 += g; s1 += g * (xv - mu) * is;
+        d0 += (double)g; d1 += (double)g * (double)((xv - mu) * is);
       }
-      if (++cnt == 64) { d0 += s0; d1 += s1; s0 = s1 = 0.f; cnt = 0; }   // bounded fp32 partials
     }
-    d0 += s0; d1 += s1;
   }
   __shared__ double sh[2][8][32];
   sh[0][threadIdx.y][threadIdx.x] = d0; sh[1][threadIdx.y][threadIdx.x] = d1;

@@ -15,6 +15,21 @@ from . import _cabi as A
 USE_TC = True
 
 
+# when a list, every convolution launch is bracketed by CUDA events: (kind, algorithmic flops, ev0, ev1)
+PROFILE = None
+
+
+def _timed(kind, flops, fn):
+    if PROFILE is None:
+        return fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = fn()
+    e1.record()
+    PROFILE.append((kind, flops, e0, e1))
+    return r
+
+
 # -------------------------------------------------------------------------------------------------
 # layout helpers
 # -------------------------------------------------------------------------------------------------
@@ -107,12 +122,14 @@ class _Conv2dFn(torch.autograd.Function):
             v1.sn = v1.sh = v1.sw = 0
         b = bias.detach() if bias is not None else None
         st = A.stream_ptr()
-        done = False
-        if USE_TC and not nchw:
-            done = A.try_call("segsde_conv2d_fwd_tc", C.byref(v1), _ref(v2), A.ptr(w), A.ptr(b), C.byref(vy),
-                              C.byref(d), st)
-        if not done:
+        flops = 2.0 * n * ho * wo * cout * kh * kw * w.shape[1]
+
+        def launch():
+            if USE_TC and not nchw and A.try_call("segsde_conv2d_fwd_tc", C.byref(v1), _ref(v2), A.ptr(w), A.ptr(b),
+                                                  C.byref(vy), C.byref(d), st):
+                return
             A.call("segsde_conv2d_fwd", C.byref(v1), _ref(v2), A.ptr(w), A.ptr(b), C.byref(vy), C.byref(d), st)
+        _timed("fprop", flops, launch)
         ctx.save_for_backward(x1, x2, w, y if act != A.ACT_NONE else None)
         ctx.cfg = (stride, pad, dil, pad_mode, up1, act, nchw, bias is not None)
         return y
@@ -142,25 +159,30 @@ class _Conv2dFn(torch.autograd.Function):
                 dx2 = cl_empty(*x2.shape, x2.device, zero=folded)
             g1 = view(dx1) if dx1 is not None else view(x1, null=True)
             g2 = (view(dx2) if dx2 is not None else view(x2, null=True)) if x2 is not None else None
-            done = False
-            if USE_TC:
-                done = A.try_call("segsde_conv2d_dgrad_tc", C.byref(vdz), A.ptr(w), C.byref(g1), _ref(g2),
-                                  C.byref(d), st)
-            if not done:
+            cneed = (x1.shape[1] if dx1 is not None else 0) + (x2.shape[1] if dx2 is not None else 0)
+            flops = 2.0 * dz.shape[0] * dz.shape[2] * dz.shape[3] * cout * kh * kw * cneed
+
+            def launch_d():
+                if USE_TC and A.try_call("segsde_conv2d_dgrad_tc", C.byref(vdz), A.ptr(w), C.byref(g1), _ref(g2),
+                                         C.byref(d), st):
+                    return
                 A.call("segsde_conv2d_dgrad", C.byref(vdz), A.ptr(w), C.byref(g1), _ref(g2), C.byref(d), st)
+            _timed("dgrad", flops, launch_d)
         if needw or (needb and has_bias):
             dw = torch.zeros_like(w)
             db = torch.zeros(cout, device=w.device, dtype=torch.float32) if has_bias else None
             v1, v2 = view(x1), (view(x2) if x2 is not None else None)
             if nchw:
                 v1.sn = v1.sh = v1.sw = 0
-            done = False
-            if USE_TC and not nchw:
-                done = A.try_call("segsde_conv2d_wgrad_tc", C.byref(v1), _ref(v2), C.byref(vdz), A.ptr(dw),
-                                  A.ptr(db), C.byref(d), st)
-            if not done:
+            flops = 2.0 * dz.shape[0] * dz.shape[2] * dz.shape[3] * cout * kh * kw * w.shape[1]
+
+            def launch_w():
+                if USE_TC and not nchw and A.try_call("segsde_conv2d_wgrad_tc", C.byref(v1), _ref(v2), C.byref(vdz),
+                                                      A.ptr(dw), A.ptr(db), C.byref(d), st):
+                    return
                 A.call("segsde_conv2d_wgrad", C.byref(v1), _ref(v2), C.byref(vdz), A.ptr(dw), A.ptr(db),
                        C.byref(d), st)
+            _timed("wgrad", flops, launch_w)
         return dx1, dx2, dw, db, None, None, None, None, None, None, None
 
 

@@ -57,19 +57,82 @@ def test_model_step_vs_reference_golden(golden, contracts, name, hw):
     losses = ml.compute_losses(inputs, out)
     vals = np.array([losses["loss/%d" % s].item() for s in range(4)] + [losses["loss"].item()])
     np.testing.assert_allclose(vals, golden[p + "losses"], rtol=5e-5)
+    # end-to-end gradient of the photometric loss: loose bound (see helpers.grad_close for why the loss
+    # gradient is only piecewise continuous); the tight per-tensor check is test_network_gradients_vs_oracle
     losses["loss"].backward()
     params = dict(model.named_parameters())
     names = [str(n) for n in golden[p + "grad_names"]]
     norms = np.array([params[n].grad.norm().item() for n in names])
     ref = golden[p + "grad_norms"]
-    bad = [(n, a, b) for n, a, b in zip(names, norms, ref) if abs(a - b) > 5e-3 * b + 1e-9]
+    bad = [(n, a, b) for n, a, b in zip(names, norms, ref) if abs(a - b) > 3e-2 * b + 1e-9]
     assert not bad, bad[:5]
-    assert rel_err(params["models.encoder.encoder.conv1.weight"].grad, golden[p + "grad_enc_conv1"]) < 5e-3
-    assert rel_err(params["models.pose.net.3.weight"].grad, golden[p + "grad_pose3"]) < 5e-3
+    assert rel_err(params["models.pose.net.3.weight"].grad, golden[p + "grad_pose3"]) < 3e-2
     sd = model.state_dict()
     assert rel_err(sd["models.encoder.encoder.bn1.running_mean"], golden[p + "bn1_running_mean"]) < 1e-5
     assert rel_err(sd["models.encoder.encoder.bn1.running_var"], golden[p + "bn1_running_var"]) < 1e-5
     assert int(sd["models.encoder.encoder.bn1.num_batches_tracked"]) == 1
+
+
+@pytest.mark.parametrize("name,hw", [("mono_r18", (64, 128)), ("mono_r50", (64, 96))])
+def test_network_gradients_vs_oracle(golden, contracts, name, hw):
+    """Backward of every network kernel in context: a smooth surrogate loss (fixed random weights on the
+    disparities and pose matrices) so that the only discontinuities are ReLU / max-pool ties; every parameter
+    gradient must match the CPU oracle's autograd to 2e-3 (relative L2 per tensor)."""
+    from improving_segmentation_with_selfsupervised_depth_b200.models.layers import Dropout
+    H, W = hw
+    B = 2
+    p = "model_%s_" % name
+    model, sd = build(contracts, name, H, W)
+    mask = unpack_mask(golden, p)
+    for mod in model.modules():
+        if isinstance(mod, Dropout):
+            mod.replay_mask = mask
+    inputs = O.synthetic_inputs(B, H, W, seed=5)
+    g = torch.Generator().manual_seed(77)
+    wd = [torch.randn(B, 1, H >> s, W >> s, generator=g) for s in range(4)]
+    wT = {f: torch.randn(B, 4, 4, generator=g) for f in (-1, 1)}
+    c = contracts[name]
+    cfg = {"num_layers": int(c["cfg"]["backbone_name"][6:]), "rswd": c["cfg"]["replace_stride_with_dilation"],
+           "frame_ids": [0, -1, 1]}
+    # The oracle is evaluated in fp32 (the reference's arithmetic) AND in fp64: ASPPPooling's BatchNorm sees
+    # B x 256 x 1 x 1 = two values per channel, which makes the encoder gradient ill-conditioned (the fp32 CPU
+    # result itself is ~1e-2 away from fp64 for ResNet-50 here), so the bound is 2e-3 + 2x the oracle's own
+    # fp32 error per tensor, measured against the fp64 result.
+    grads = {}
+    for dt in (torch.float32, torch.float64):
+        osd = {k: (v.to(dt) if v.dtype.is_floating_point else v).clone().requires_grad_(
+            v.dtype.is_floating_point and "running" not in k) for k, v in sd.items()}
+        inp = {k: v.to(dt) for k, v in inputs.items()}
+        old = torch.get_default_dtype()
+        torch.set_default_dtype(dt)
+        try:
+            ref = O.model_forward(osd, inp, cfg, O.BNMode(True), dropout_mask=mask.to(dt))
+            rl = sum((ref[("disp", s)] * wd[s].to(dt)).sum() for s in range(4)) + \
+                100 * sum((ref[("cam_T_cam", 0, f)] * wT[f].to(dt)).sum() for f in (-1, 1))
+            rl.backward()
+        finally:
+            torch.set_default_dtype(old)
+        grads[dt] = {k: v.grad.double() for k, v in osd.items() if v.grad is not None}
+    gin = {k: v.cuda() for k, v in inputs.items()}
+    with contextlib.redirect_stdout(io.StringIO()):
+        out = model(gin)
+    # weighted sums via the library's own scale/accumulate entry point would hide nothing: use torch for the
+    # test-side reduction only
+    gl = sum((out[("disp", s)] * wd[s].cuda()).sum() for s in range(4)) + \
+        100 * sum((out[("cam_T_cam", 0, f)] * wT[f].cuda()).sum() for f in (-1, 1))
+    assert abs(gl.item() - rl.item()) < 1e-3 * abs(rl.item()) + 1e-3
+    gl.backward()
+    bad = []
+    for n, q in model.named_parameters():
+        if n not in grads[torch.float64]:
+            assert q.grad is None or q.grad.abs().max().item() == 0, n
+            continue
+        r64, r32 = grads[torch.float64][n], grads[torch.float32][n]
+        own = ((r32 - r64).norm() / (r64.norm() + 1e-12)).item()
+        e = ((q.grad.double().cpu() - r64).norm() / (r64.norm() + 1e-12)).item()
+        if e > 2e-3 + 2 * own:
+            bad.append((n, e, own))
+    assert not bad, bad[:8]
 
 
 def test_frozen_encoder_and_eval_mode(contracts):
@@ -83,7 +146,8 @@ def test_frozen_encoder_and_eval_mode(contracts):
         out = model(inputs)
     (out[("disp", 0)].mean() + out[("cam_T_cam", 0, 1)].sum()).backward()
     assert all(q.grad is None for q in model.models["encoder"].parameters())
-    assert all(q.grad is not None for q in model.models["depth"].parameters())
+    assert model.models["depth"].convs[("upconv", 0, 1)].block[0].conv.weight.grad is not None
+    assert model.models["pose"].net[3].weight.grad is not None
     model.eval()
     with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
         ev = model(inputs)
