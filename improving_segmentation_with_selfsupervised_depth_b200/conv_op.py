@@ -1,0 +1,169 @@
+"""Convolution autograd op: routes every eligible conv to the tcgen05/TMA kernels (conv_tc.cu) and the
+rest (3/6-channel stem, C->1 disparity heads, 12-channel pose output, stride 2) to the generic CUDA-core
+kernels (conv_simt.cu).
+
+Tensor-core route for the decoder's fused inputs: reflection padding and nearest x2 upsampling are
+materialised once into a halo-padded NHWC buffer (`segsde_pad_prep`), after which the convolution is a
+plain "valid" one whose taps are TMA boxes at shifted coordinates; the concat stays virtual (second
+tensor map).  Backward: dgrad = the same fprop kernel on dy with the transposed / tap-flipped weights, the
+halo buffer's gradient is folded back with `segsde_pad_fold`, wgrad reads the saved padded buffers.
+"""
+import ctypes as C
+
+import torch
+
+from . import _cabi as A
+from . import ops
+
+
+def _tc_enabled():
+    return ops.USE_TC and A.lib().segsde_tc_available() == 1
+
+
+def _prep(x, up, pad):
+    n, c, h, w = x.shape
+    f = 2 if up else 1
+    y = ops.cl_empty(n, c, h * f + 2 * pad, w * f + 2 * pad, x.device)
+    A.call("segsde_pad_prep", C.byref(ops.view(x)), C.byref(ops.view(y)), C.c_int(int(up)), C.c_int(pad),
+           A.stream_ptr())
+    return y
+
+
+def _fwd(x1, x2, w, b, y, d, kind, flops):
+    st = A.stream_ptr()
+    v1, v2, vy = ops.view(x1), (ops.view(x2) if x2 is not None else None), ops.view(y)
+    if d.nchw_norm_in:
+        v1.sn = v1.sh = v1.sw = 0
+
+    def launch():
+        if _tc_enabled() and A.try_call("segsde_conv2d_fwd_tc", C.byref(v1), ops._ref(v2), A.ptr(w), A.ptr(b),
+                                        C.byref(vy), C.byref(d), st):
+            return
+        A.call("segsde_conv2d_fwd", C.byref(v1), ops._ref(v2), A.ptr(w), A.ptr(b), C.byref(vy), C.byref(d), st)
+    ops._timed(kind, flops, launch)
+
+
+class _Conv2dFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x1, x2, weight, bias, stride, pad, dil, pad_mode, up1, act, nchw):
+        A.require_cuda(x1, weight)
+        if nchw:
+            x1 = x1.contiguous()
+            x2 = x2.contiguous() if x2 is not None else None
+        else:
+            x1 = ops.as_cl(x1)
+            x2 = ops.as_cl(x2) if x2 is not None else None
+        w = ops.ohwi(weight.detach())
+        cout, ctot, kh, kw = w.shape
+        n, c1, h1, w1 = x1.shape
+        c2 = x2.shape[1] if x2 is not None else 0
+        hc, wc = (h1 * 2, w1 * 2) if up1 else (h1, w1)
+        ho, wo = ops._conv_out_hw(hc, wc, kh, kw, stride, pad, dil)
+        reflect = pad_mode == A.PAD_REFLECT
+        tc_shape = (not nchw and stride == 1 and c1 % 32 == 0 and c2 % 32 == 0 and cout % 64 == 0 and _tc_enabled())
+        prepped = tc_shape and (reflect or up1) and pad > 0
+        if prepped:          # materialise padding (+ upsampling); the conv becomes a plain valid one
+            x1e = _prep(x1, up1, pad)
+            x2e = _prep(x2, False, pad) if x2 is not None else None
+            pad_e, mode_e, up_e = 0, A.PAD_ZERO, False
+        else:
+            x1e, x2e, pad_e, mode_e, up_e = x1, x2, pad, pad_mode, up1
+        y = ops.cl_empty(n, cout, ho, wo, x1.device)
+        d = ops._desc(kh, kw, stride, pad_e, dil, mode_e, up_e, act, nchw)
+        b = bias.detach() if bias is not None else None
+        _fwd(x1e, x2e, w, b, y, d, "fprop", 2.0 * n * ho * wo * cout * kh * kw * ctot)
+        ctx.save_for_backward(x1e, x2e, w, y if act != A.ACT_NONE else None)
+        ctx.cfg = (stride, pad, dil, pad_mode, up1, act, nchw, bias is not None, prepped, pad_e, mode_e, up_e,
+                   tuple(x1.shape), tuple(x2.shape) if x2 is not None else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x1e, x2e, w, y = ctx.saved_tensors
+        (stride, pad, dil, pad_mode, up1, act, nchw, has_bias, prepped, pad_e, mode_e, up_e, shp1, shp2) = ctx.cfg
+        cout, ctot, kh, kw = w.shape
+        st = A.stream_ptr()
+        dy = ops.as_cl(dy)
+        need1, need2, needw, needb = ctx.needs_input_grad[:4]
+        dev = dy.device
+        db = torch.zeros(cout, device=dev, dtype=torch.float32) if (has_bias and needb) else None
+        if act != A.ACT_NONE or db is not None:
+            dz = ops.cl_empty(*dy.shape, dev) if act != A.ACT_NONE else None
+            A.call("segsde_act_bwd_bias", ops._ref(ops.view(y)) if y is not None else None, C.byref(ops.view(dy)),
+                   ops._ref(ops.view(dz)) if dz is not None else None, C.c_int(act), A.ptr(db), st)
+            if dz is None:
+                dz = dy
+        else:
+            dz = dy
+        n, _, ho, wo = dz.shape
+        c1 = x1e.shape[1]
+        c2 = x2e.shape[1] if x2e is not None else 0
+        d = ops._desc(kh, kw, stride, pad_e, dil, mode_e, up_e, A.ACT_NONE, nchw)
+        dx1 = dx2 = dw = None
+
+        # ---- dgrad ---------------------------------------------------------------------------------
+        if (need1 or (need2 and x2e is not None)) and not nchw:
+            tc_dgrad = (_tc_enabled() and stride == 1 and mode_e == A.PAD_ZERO and not up_e and cout % 32 == 0
+                        and dil * (kh - 1) - pad_e >= 0)
+            results = []
+            for need, xe, c0, cn in ((need1, x1e, 0, c1), (need2 and x2e is not None, x2e, c1, c2)):
+                if not need:
+                    results.append(None)
+                    continue
+                if tc_dgrad and cn % 64 == 0:
+                    wt = torch.empty(cn * kh * kw * cout, device=dev, dtype=torch.float32)
+                    A.call("segsde_weight_transpose_flip", A.ptr(w), A.ptr(wt), C.c_int(cout), C.c_int(kh), C.c_int(kw),
+                           C.c_int(ctot), C.c_int(c0), C.c_int(cn), st)
+                    gx = ops.cl_empty(*xe.shape, dev)
+                    dd = ops._desc(kh, kw, 1, dil * (kh - 1) - pad_e, dil, A.PAD_ZERO, False, A.ACT_NONE, False)
+                    _fwd(dz, None, wt, None, gx, dd, "dgrad", 2.0 * n * ho * wo * cout * kh * kw * cn)
+                    results.append(gx)
+                else:
+                    results.append("generic")
+            if "generic" in results:
+                folded = mode_e == A.PAD_REFLECT or up_e
+                g1 = ops.cl_empty(*x1e.shape, dev, zero=folded) if results[0] == "generic" else None
+                g2 = ops.cl_empty(*x2e.shape, dev, zero=folded) if (x2e is not None and results[1] == "generic") else None
+                v1 = ops.view(g1) if g1 is not None else ops.view(x1e, null=True)
+                v2 = (ops.view(g2) if g2 is not None else ops.view(x2e, null=True)) if x2e is not None else None
+                cneed = (c1 if g1 is not None else 0) + (c2 if g2 is not None else 0)
+                ops._timed("dgrad", 2.0 * n * ho * wo * cout * kh * kw * cneed,
+                           lambda: A.call("segsde_conv2d_dgrad", C.byref(ops.view(dz)), A.ptr(w), C.byref(v1),
+                                          ops._ref(v2), C.byref(d), st))
+                if g1 is not None:
+                    results[0] = g1
+                if g2 is not None:
+                    results[1] = g2
+            dx1, dx2 = results[0], results[1]
+            if prepped:          # fold the halo / upsampling back onto the original tensors
+                if dx1 is not None:
+                    f = ops.cl_empty(*shp1, dev)
+                    A.call("segsde_pad_fold", C.byref(ops.view(dx1)), C.byref(ops.view(f)), C.c_int(int(up1)),
+                           C.c_int(pad), st)
+                    dx1 = f
+                if dx2 is not None:
+                    f = ops.cl_empty(*shp2, dev)
+                    A.call("segsde_pad_fold", C.byref(ops.view(dx2)), C.byref(ops.view(f)), C.c_int(0), C.c_int(pad), st)
+                    dx2 = f
+
+        # ---- wgrad (+ bias gradient on the generic path) ------------------------------------------------
+        if needw:
+            dw = torch.zeros_like(w)
+            v1, v2 = ops.view(x1e), (ops.view(x2e) if x2e is not None else None)
+            if nchw:
+                v1.sn = v1.sh = v1.sw = 0
+            vdz = ops.view(dz)
+
+            def launch_w():
+                if _tc_enabled() and not nchw and A.try_call("segsde_conv2d_wgrad_tc", C.byref(v1), ops._ref(v2),
+                                                             C.byref(vdz), A.ptr(dw), None, C.byref(d), st):
+                    return
+                A.call("segsde_conv2d_wgrad", C.byref(v1), ops._ref(v2), C.byref(vdz), A.ptr(dw), None, C.byref(d), st)
+            ops._timed("wgrad", 2.0 * n * ho * wo * cout * kh * kw * ctot, launch_w)
+        return dx1, dx2, dw, db, None, None, None, None, None, None, None
+
+
+def conv2d(x1, weight, bias=None, x2=None, stride=1, pad=0, dil=1, pad_mode=A.PAD_ZERO, up1=False,
+           act=A.ACT_NONE, nchw_norm_in=False):
+    """y = act(conv(cat(up?(x1), x2)) + bias) — see segsde_conv2d_fwd / segsde_conv2d_fwd_tc."""
+    return _Conv2dFn.apply(x1, x2, weight, bias, stride, pad, dil, pad_mode, up1, act, nchw_norm_in)

@@ -1,0 +1,138 @@
+// Helpers around the tensor-core convolution family: materialised reflection padding (+ nearest x2
+// upsampling) of a conv input and its adjoint, the transposed / tap-flipped weight matrix that turns dgrad
+// into an fprop, and the fused activation-backward + bias-gradient pass.
+#include "common.cuh"
+
+namespace segsde {
+
+// y[n, hp, wp, c] = x[n, refl(hp - pad) >> up, refl(wp - pad) >> up, c]
+__global__ void pad_prep_kernel(View x, View y, int up, int pad, int Hc, int Wc) {
+  const int cq = y.c / 4;
+  const long long total = (long long)y.n * y.h * y.w * cq;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % cq) * 4; long long q = idx / cq;
+  const int wp = (int)(q % y.w); q /= y.w;
+  const int hp = (int)(q % y.h); const int n = (int)(q / y.h);
+  const int h = reflect_idx(hp - pad, Hc) >> up, w = reflect_idx(wp - pad, Wc) >> up;
+  *reinterpret_cast<float4*>(y.p + y.off(n, hp, wp) + c) =
+      *reinterpret_cast<const float4*>(x.p + x.off(n, h, w) + c);
+}
+
+// adjoint of pad_prep: dx[n,h,w,c] = sum over the (1<<up)^2 fine positions of the sum over their reflect preimages
+__global__ void pad_fold_kernel(View dyp, View dx, int up, int pad, int Hc, int Wc) {
+  const int cq = dx.c / 4;
+  const long long total = (long long)dx.n * dx.h * dx.w * cq;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % cq) * 4; long long q = idx / cq;
+  const int w = (int)(q % dx.w); q /= dx.w;
+  const int h = (int)(q % dx.h); const int n = (int)(q / dx.h);
+  const int f = 1 << up;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int a = 0; a < f; ++a) {
+    const int hh = h * f + a;
+    int rows[3]; int nr = 0;
+    rows[nr++] = hh;
+    if (hh >= 1 && hh <= pad) rows[nr++] = -hh;
+    if (hh >= Hc - 1 - pad && hh <= Hc - 2) rows[nr++] = 2 * (Hc - 1) - hh;
+    for (int b = 0; b < f; ++b) {
+      const int ww = w * f + b;
+      int cols[3]; int nc = 0;
+      cols[nc++] = ww;
+      if (ww >= 1 && ww <= pad) cols[nc++] = -ww;
+      if (ww >= Wc - 1 - pad && ww <= Wc - 2) cols[nc++] = 2 * (Wc - 1) - ww;
+      for (int i = 0; i < nr; ++i)
+        for (int j = 0; j < nc; ++j) {
+          const float4 v = *reinterpret_cast<const float4*>(dyp.p + dyp.off(n, rows[i] + pad, cols[j] + pad) + c);
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    }
+  }
+  *reinterpret_cast<float4*>(dx.p + dx.off(n, h, w) + c) = acc;
+}
+
+// wt[ci - c0][kh-1-r][kw-1-s][co] = w[co][r][s][ci]
+__global__ void weight_tflip_kernel(const float* __restrict__ w, float* __restrict__ wt, int Cout, int kh, int kw,
+                                    int Ctot, int c0, int cn) {
+  const long long total = (long long)cn * kh * kw * Cout;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int co = (int)(idx % Cout); long long q = idx / Cout;
+  const int s = (int)(q % kw); q /= kw;
+  const int r = (int)(q % kh); const int ci = (int)(q / kh);
+  wt[idx] = w[(((long long)co * kh + (kh - 1 - r)) * kw + (kw - 1 - s)) * Ctot + c0 + ci];
+}
+
+// dz = dy * act'(y) ; dbias[c] += sum dz   (block = 32 channels x 8 pixel lanes, like the BN reductions)
+__global__ void __launch_bounds__(256) act_bwd_bias_kernel(View y, View dy, View dz, int act, float* __restrict__ dbias,
+                                                           long long slab) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const long long P = (long long)dy.n * dy.h * dy.w;
+  const long long pbeg = (long long)blockIdx.y * slab, pend = min(P, pbeg + slab);
+  float s = 0.f;
+  if (c < dy.c) {
+    for (long long p = pbeg + threadIdx.y; p < pend; p += 8) {
+      const int w = (int)(p % dy.w); const long long q = p / dy.w;
+      const int h = (int)(q % dy.h), n = (int)(q / dy.h);
+      float g = dy.p[dy.off(n, h, w) + c];
+      if (act != SEGSDE_ACT_NONE) g *= act_grad_from_out(y.p[y.off(n, h, w) + c], act);
+      if (dz.p) dz.p[dz.off(n, h, w) + c] = g;
+      s += g;
+    }
+  }
+  __shared__ float sh[8][32];
+  sh[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (dbias && threadIdx.y == 0 && c < dy.c) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x];
+    atomicAdd(dbias + c, t);
+  }
+}
+
+}  // namespace segsde
+using namespace segsde;
+
+extern "C" int segsde_pad_prep(const segsde_nhwc_t* x, const segsde_nhwc_t* y, int up, int pad, void* stream) {
+  if (!x || !y || !x->ptr || !y->ptr || pad < 0 || (up != 0 && up != 1)) return SEGSDE_E_ARG;
+  View vx = mk(x), vy = mk(y);
+  const int Hc = vx.h << up, Wc = vx.w << up;
+  if (vy.h != Hc + 2 * pad || vy.w != Wc + 2 * pad || vy.c != vx.c || vy.n != vx.n || pad >= Hc || pad >= Wc) return SEGSDE_E_ARG;
+  if (!vec4_ok(vx) || !vec4_ok(vy)) return SEGSDE_E_ALIGN;
+  const long long total = (long long)vy.n * vy.h * vy.w * (vy.c / 4);
+  pad_prep_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(vx, vy, up, pad, Hc, Wc);
+  return launched();
+}
+extern "C" int segsde_pad_fold(const segsde_nhwc_t* dyp, const segsde_nhwc_t* dx, int up, int pad, void* stream) {
+  if (!dyp || !dx || !dyp->ptr || !dx->ptr || pad < 0 || (up != 0 && up != 1)) return SEGSDE_E_ARG;
+  View vd = mk(dyp), vx = mk(dx);
+  const int Hc = vx.h << up, Wc = vx.w << up;
+  if (vd.h != Hc + 2 * pad || vd.w != Wc + 2 * pad || vd.c != vx.c || vd.n != vx.n) return SEGSDE_E_ARG;
+  if (!vec4_ok(vx) || !vec4_ok(vd)) return SEGSDE_E_ALIGN;
+  const long long total = (long long)vx.n * vx.h * vx.w * (vx.c / 4);
+  pad_fold_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(vd, vx, up, pad, Hc, Wc);
+  return launched();
+}
+extern "C" int segsde_weight_transpose_flip(const float* w, float* wt, int cout, int kh, int kw, int ctot,
+                                            int c_begin, int c_count, void* stream) {
+  if (!w || !wt || cout < 1 || kh < 1 || kw < 1 || c_begin < 0 || c_count < 1 || c_begin + c_count > ctot) return SEGSDE_E_ARG;
+  const long long total = (long long)c_count * kh * kw * cout;
+  weight_tflip_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(w, wt, cout, kh, kw, ctot, c_begin, c_count);
+  return launched();
+}
+extern "C" int segsde_act_bwd_bias(const segsde_nhwc_t* y, const segsde_nhwc_t* dy, const segsde_nhwc_t* dz, int act,
+                                   float* dbias, void* stream) {
+  if (!dy || !dy->ptr) return SEGSDE_E_ARG;
+  View vy = mk(y), vd = mk(dy), vz = mk(dz);
+  if (act != SEGSDE_ACT_NONE && (!vy.p || !same_shape(vy, vd))) return SEGSDE_E_ARG;
+  if (vz.p && !same_shape(vz, vd)) return SEGSDE_E_ARG;
+  const long long P = (long long)vd.n * vd.h * vd.w;
+  const int groups = cdiv(vd.c, 32);
+  long long want = (148LL * 8) / groups; if (want < 1) want = 1;
+  long long s = cdiv(P, 64); if (s > want) s = want; if (s < 1) s = 1;
+  const long long slab = (P + s - 1) / s;
+  dim3 grid(groups, cdiv(P, slab)), block(32, 8);
+  act_bwd_bias_kernel<<<grid, block, 0, as_stream(stream)>>>(vy, vd, vz, act, dbias, slab);
+  return launched();
+}

@@ -1,9 +1,524 @@
-// placeholder — replaced by the tcgen05 implicit-GEMM family
+// tcgen05 / TMEM / TMA implicit-GEMM convolutions for sm_100a (TF32 operands, FP32 accumulate — the
+// numerics class of the reference's own cuDNN path, which allows TF32 by default).
+//
+//   fprop / dgrad  (tc_conv_kernel):   D[pixels(128) x Cout(BN)] += A_tap[pixels x 32ch] * B_tap[32ch x BN]
+//       A: TMA 4-D box (32 ch, BW, BH, 1) of the NHWC activation at the tap-shifted coordinate; zero padding
+//          is the TMA out-of-bounds fill, stride 2 is the tensor map's element stride, a channel concat is a
+//          second tensor map.  K-major, SWIZZLE_128B.
+//       B: TMA 2-D box (32 k, BN) of the [Cout][kh*kw*Cin] weight matrix.  K-major, SWIZZLE_128B.
+//       dgrad is the same kernel run on dy with the transposed + tap-flipped weight matrix.
+//   wgrad (tc_wgrad_kernel):  dW^T[(tap,ci)(128) x Cout(BN)] += X_tap[32 px x 128 (tap,ci)]^T * dY[32 px x BN]
+//       both operands MN-major straight out of NHWC (pixels are the GEMM-K), split over pixel ranges,
+//       partial sums reduced with red.global.add.f32.
+//
+// Warp roles (256 threads, 1 CTA / SM, persistent): warp 0 = TMA producer, warp 1 = MMA issuer (one elected
+// lane), warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> bias/activation -> global).
+// Accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cuda.h>
+
 #include "common.cuh"
-extern "C" int segsde_tc_available(void) { return 0; }
-extern "C" int segsde_conv2d_fwd_tc(const segsde_nhwc_t*, const segsde_nhwc_t*, const float*, const float*,
-                                    const segsde_nhwc_t*, const segsde_conv_desc_t*, void*) { return SEGSDE_E_UNSUPPORTED; }
-extern "C" int segsde_conv2d_dgrad_tc(const segsde_nhwc_t*, const float*, const segsde_nhwc_t*,
-                                      const segsde_nhwc_t*, const segsde_conv_desc_t*, void*) { return SEGSDE_E_UNSUPPORTED; }
-extern "C" int segsde_conv2d_wgrad_tc(const segsde_nhwc_t*, const segsde_nhwc_t*, const segsde_nhwc_t*, float*,
-                                      float*, const segsde_conv_desc_t*, void*) { return SEGSDE_E_UNSUPPORTED; }
+
+namespace segsde {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor, SWIZZLE_128B (cute::UMMA::SmemDescriptor: version 1, layout type 2)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor for kind::tf32, fp32 accumulate, M = 128
+__host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+constexpr int STAGES = 6;
+constexpr int A_BYTES = 128 * 128;        // 128 rows x 32 fp32
+constexpr int NT = 256;
+
+struct TcConvP {
+  View y;                     // output view
+  const float* bias;
+  int act;
+  int C[2];                   // channels of the two sources (multiples of 32; C[1] may be 0)
+  int Ctot, Cout;
+  int kh, kw, stride, pad, dil;
+  int Ho, Wo, N;
+  int BW, BH, tiles_w, tiles_h, tiles_n;   // pixel tile = BW x BH (=128), tiles_n = Cout / BN
+  long long total_tiles;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NT, 1)
+tc_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+               const __grid_constant__ CUtensorMap tmB, const TcConvP p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int B_BYTES = BN * 128;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]);
+  const uint32_t tfull0 = smem_u32(&bars[2 * STAGES]), tempty0 = smem_u32(&bars[2 * STAGES + 2]);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tma_prefetch_desc(&tmA0); tma_prefetch_desc(&tmB);
+    if (p.C[1]) tma_prefetch_desc(&tmA1);
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"(2 * BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const int kchunks = p.Ctot / 32;
+  const int kiters = p.kh * p.kw * kchunks;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const int tn = (int)(t % p.tiles_n); long long q = t / p.tiles_n;
+        const int tw = (int)(q % p.tiles_w); q /= p.tiles_w;
+        const int th = (int)(q % p.tiles_h); const int n = (int)(q / p.tiles_h);
+        const int w0 = tw * p.BW, h0 = th * p.BH;
+        for (int tap = 0; tap < p.kh * p.kw; ++tap) {
+          const int r = tap / p.kw, s = tap % p.kw;
+          const int wi = w0 * p.stride - p.pad + s * p.dil, hi = h0 * p.stride - p.pad + r * p.dil;
+          for (int kc = 0; kc < kchunks; ++kc) {
+            mbar_wait(empty0 + 8 * stage, phase ^ 1);
+            const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES), sb = sa + A_BYTES;
+            const uint32_t fb = full0 + 8 * stage;
+            mbar_expect_tx(fb, STAGE_BYTES);
+            const int c = kc * 32;
+            if (c < p.C[0]) tma_load_4d(sa, &tmA0, fb, c, wi, hi, n);
+            else tma_load_4d(sa, &tmA1, fb, c - p.C[0], wi, hi, n);
+            tma_load_2d(sb, &tmB, fb, tap * p.Ctot + c, tn * BN);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc(BN, 0, 0);
+    int stage = 0; uint32_t phase = 0;
+    int as = 0; uint32_t aphase = 0;
+    for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      mbar_wait(tempty0 + 8 * as, aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * BN;
+      for (int it = 0; it < kiters; ++it) {
+        mbar_wait(full0 + 8 * stage, phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES), sb = sa + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {   // UMMA_K = 8 tf32 = 32 bytes inside the 128-byte swizzle row
+            const uint64_t ad = make_desc(sa + 32 * k, 16, 1024), bd = make_desc(sb + 32 * k, 16, 1024);
+            tc_mma_tf32(d_tmem, ad, bd, idesc, (it | k) != 0);
+          }
+          tc_commit(empty0 + 8 * stage);            // frees the smem slot when these MMAs retire
+          if (it == kiters - 1) tc_commit(tfull0 + 8 * as);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp - 4;                 // TMEM lane quarter
+    const int m = q * 32 + lane;
+    int as = 0; uint32_t aphase = 0;
+    for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const int tn = (int)(t % p.tiles_n); long long qq = t / p.tiles_n;
+      const int tw = (int)(qq % p.tiles_w); qq /= p.tiles_w;
+      const int th = (int)(qq % p.tiles_h); const int n = (int)(qq / p.tiles_h);
+      const int h = th * p.BH + m / p.BW, w = tw * p.BW + m % p.BW;
+      const bool valid = h < p.Ho && w < p.Wo;
+      float* out = p.y.p + p.y.off(n, valid ? h : 0, valid ? w : 0) + tn * BN;
+      mbar_wait(tfull0 + 8 * as, aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < BN / 32; ++cc) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + cc * 32, v);
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 o;
+            const int c = tn * BN + cc * 32 + j * 4;
+            o.x = act_apply(v[4 * j + 0] + (p.bias ? __ldg(p.bias + c + 0) : 0.f), p.act);
+            o.y = act_apply(v[4 * j + 1] + (p.bias ? __ldg(p.bias + c + 1) : 0.f), p.act);
+            o.z = act_apply(v[4 * j + 2] + (p.bias ? __ldg(p.bias + c + 2) : 0.f), p.act);
+            o.w = act_apply(v[4 * j + 3] + (p.bias ? __ldg(p.bias + c + 3) : 0.f), p.act);
+            *reinterpret_cast<float4*>(out + cc * 32 + j * 4) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * as);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// wgrad
+// ------------------------------------------------------------------------------------------------
+struct TcWgradP {
+  float* dw;                  // [Cout][Ktot]
+  int C[2], Ctot, Cout, Ktot;
+  int kh, kw, pad, dil;
+  int Ho, Wo, N;
+  int wchunks;                // Wo / 32
+  long long chunks;           // N * Ho * wchunks
+  int mtiles, ntiles, splits;
+  long long chunks_per_split;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NT, 1)
+tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1,
+                const __grid_constant__ CUtensorMap tmDy, const TcWgradP p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int B_BYTES = BN * 128;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
+  __shared__ uint32_t tmem_base_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]), tfull = smem_u32(&bars[2 * STAGES]);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+    mbar_init(tfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tma_prefetch_desc(&tmX0); tma_prefetch_desc(&tmDy);
+    if (p.C[1]) tma_prefetch_desc(&tmX1);
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"(BN < 32 ? 32 : BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  // work item: (mt, nt, split)
+  int b = blockIdx.x;
+  const int split = b % p.splits; b /= p.splits;
+  const int nt = b % p.ntiles; const int mt = b / p.ntiles;
+  const long long c_beg = (long long)split * p.chunks_per_split;
+  const long long c_end = min(p.chunks, c_beg + p.chunks_per_split);
+  const int niter = (int)max(0LL, c_end - c_beg);
+  // the 4 (tap, channel-chunk) groups that make up this CTA's 128 GEMM-M rows
+  const int ngroups = min(4, (p.Ktot - mt * 128 + 31) / 32);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int g_src[4], g_c[4], g_dw[4], g_dh[4];
+      for (int g = 0; g < 4; ++g) {
+        const int kf = (mt * 4 + g) * 32;
+        const int kk = kf < p.Ktot ? kf : 0;
+        const int tap = kk / p.Ctot, coff = kk % p.Ctot;
+        g_src[g] = coff < p.C[0] ? 0 : 1;
+        g_c[g] = g_src[g] ? coff - p.C[0] : coff;
+        g_dh[g] = -p.pad + (tap / p.kw) * p.dil;
+        g_dw[g] = -p.pad + (tap % p.kw) * p.dil;
+      }
+      for (long long ch = c_beg; ch < c_end; ++ch) {
+        const int wc = (int)(ch % p.wchunks); long long q = ch / p.wchunks;
+        const int h = (int)(q % p.Ho); const int n = (int)(q / p.Ho);
+        const int w0 = wc * 32;
+        mbar_wait(empty0 + 8 * stage, phase ^ 1);
+        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES), sb = sa + A_BYTES;
+        const uint32_t fb = full0 + 8 * stage;
+        mbar_expect_tx(fb, (ngroups + BN / 32) * 4096);
+        for (int g = 0; g < ngroups; ++g)
+          tma_load_4d(sa + g * 4096, g_src[g] ? &tmX1 : &tmX0, fb, g_c[g], w0 + g_dw[g], h + g_dh[g], n);
+#pragma unroll
+        for (int j = 0; j < BN / 32; ++j) tma_load_4d(sb + j * 4096, &tmDy, fb, nt * BN + j * 32, w0, h, n);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc(BN, 1, 1);
+    int stage = 0; uint32_t phase = 0;
+    for (int it = 0; it < niter; ++it) {
+      mbar_wait(full0 + 8 * stage, phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES), sb = sa + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {     // 8 pixels (= one 8-row swizzle group, 1024 B) per MMA
+          const uint64_t ad = make_desc(sa + 1024 * k, 4096, 1024), bd = make_desc(sb + 1024 * k, 4096, 1024);
+          tc_mma_tf32(tmem_base, ad, bd, idesc, (it | k) != 0);
+        }
+        tc_commit(empty0 + 8 * stage);
+        if (it == niter - 1) tc_commit(tfull);
+      }
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp >= 4 && niter > 0) {
+    const int q = warp - 4;
+    const int m = q * 32 + lane;
+    const int kf = mt * 128 + m;
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int cc = 0; cc < BN / 32; ++cc) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + cc * 32, v);
+      if (kf < p.Ktot) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int co = nt * BN + cc * 32 + j;
+          atomicAdd(p.dw + (long long)co * p.Ktot + kf, v[j]);   // lanes = consecutive kf -> coalesced RED
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN < 32 ? 32 : BN));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static int g_encode_state = 0;   // 0 unknown, 1 ok, -1 unavailable
+
+static bool tc_init() {
+  if (g_encode_state == 0) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && fn && qres == cudaDriverEntryPointSuccess) { g_encode = (EncodeTiledFn)fn; g_encode_state = 1; }
+    else { cudaGetLastError(); g_encode_state = -1; }
+  }
+  return g_encode_state == 1;
+}
+
+// NHWC activation view -> 4-D map (C, W, H, N), box (32, bw, bh, 1), optional element stride on W/H
+static bool make_act_map(CUtensorMap* m, const View& v, int bw, int bh, int estride) {
+  if ((reinterpret_cast<uintptr_t>(v.p) & 15) || (v.sw % 4) || (v.sh % 4) || (v.sn % 4) || (v.c % 4)) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)v.c, (cuuint64_t)v.w, (cuuint64_t)v.h, (cuuint64_t)v.n};
+  cuuint64_t strides[3] = {(cuuint64_t)v.sw * 4, (cuuint64_t)v.sh * 4, (cuuint64_t)v.sn * 4};
+  cuuint32_t box[4] = {32, (cuuint32_t)(bw * estride), (cuuint32_t)(bh * estride), 1};
+  cuuint32_t es[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
+  if (box[1] > 256 || box[2] > 256) return false;
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, v.p, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+static bool make_w_map(CUtensorMap* m, const float* w, int ktot, int cout, int bn) {
+  if ((reinterpret_cast<uintptr_t>(w) & 15) || (ktot % 4)) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)cout};
+  cuuint64_t strides[1] = {(cuuint64_t)ktot * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)bn};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)w, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
+  return n;
+}
+
+template <int BN>
+static int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcConvP& p, cudaStream_t st) {
+  constexpr int smem = STAGES * (A_BYTES + BN * 128) + 1024;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(tc_conv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+  long long grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  tc_conv_kernel<BN><<<(int)grid, NT, smem, st>>>(a0, a1, b, p);
+  return launched();
+}
+template <int BN>
+static int launch_wgrad(const CUtensorMap& x0, const CUtensorMap& x1, const CUtensorMap& dy, const TcWgradP& p, cudaStream_t st) {
+  constexpr int smem = STAGES * (A_BYTES + BN * 128) + 1024;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(tc_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+  tc_wgrad_kernel<BN><<<p.mtiles * p.ntiles * p.splits, NT, smem, st>>>(x0, x1, dy, p);
+  return launched();
+}
+
+static int pow2_floor(int v) { int r = 1; while (r * 2 <= v) r *= 2; return r; }
+
+}  // namespace segsde
+using namespace segsde;
+
+extern "C" int segsde_tc_available(void) { return tc_init() ? 1 : 0; }
+
+// y = act(conv(cat(x1, x2), w) + bias), zero padding, stride 1 or 2, any dilation; channel counts multiples
+// of 32 (inputs) / 64 (outputs).  Anything else -> SEGSDE_E_UNSUPPORTED (caller uses the generic path).
+extern "C" int segsde_conv2d_fwd_tc(const segsde_nhwc_t* x1, const segsde_nhwc_t* x2, const float* w,
+                                    const float* bias, const segsde_nhwc_t* y, const segsde_conv_desc_t* d,
+                                    void* stream) {
+  if (!x1 || !x1->ptr || !w || !y || !y->ptr || !d) return SEGSDE_E_ARG;
+  if (!tc_init()) return SEGSDE_E_UNSUPPORTED;
+  if (d->pad_mode != SEGSDE_PAD_ZERO || d->up1 || d->nchw_norm_in) return SEGSDE_E_UNSUPPORTED;
+  if (d->stride != 1) return SEGSDE_E_UNSUPPORTED;   // stride 2 (TMA element strides) not enabled yet
+  View v1 = mk(x1), v2 = mk(x2), vy = mk(y);
+  const int C1 = v1.c, C2 = v2.p ? v2.c : 0, Cout = vy.c;
+  if (C1 % 32 || C2 % 32 || Cout % 64) return SEGSDE_E_UNSUPPORTED;
+  if (v2.p && (v2.h != v1.h || v2.w != v1.w || v2.n != v1.n)) return SEGSDE_E_ARG;
+  const int Ho = (v1.h + 2 * d->pad - d->dil * (d->kh - 1) - 1) / d->stride + 1;
+  const int Wo = (v1.w + 2 * d->pad - d->dil * (d->kw - 1) - 1) / d->stride + 1;
+  if (vy.h != Ho || vy.w != Wo || vy.n != v1.n) return SEGSDE_E_ARG;
+  if (!vec4_ok(vy)) return SEGSDE_E_UNSUPPORTED;
+  const int BN = (Cout % 128 == 0) ? 128 : 64;
+  TcConvP p;
+  p.y = vy; p.bias = bias; p.act = d->act;
+  p.C[0] = C1; p.C[1] = C2; p.Ctot = C1 + C2; p.Cout = Cout;
+  p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pad = d->pad; p.dil = d->dil;
+  p.Ho = Ho; p.Wo = Wo; p.N = v1.n;
+  p.BW = Wo >= 128 ? 128 : pow2_floor(Wo < 1 ? 1 : Wo);
+  if (p.BW < 8) return SEGSDE_E_UNSUPPORTED;
+  p.BH = 128 / p.BW;
+  p.tiles_w = cdiv(Wo, p.BW); p.tiles_h = cdiv(Ho, p.BH); p.tiles_n = Cout / BN;
+  p.total_tiles = (long long)p.tiles_w * p.tiles_h * p.N * p.tiles_n;
+  CUtensorMap a0, a1, b;
+  if (!make_act_map(&a0, v1, p.BW, p.BH, d->stride)) return SEGSDE_E_UNSUPPORTED;
+  if (C2) { if (!make_act_map(&a1, v2, p.BW, p.BH, d->stride)) return SEGSDE_E_UNSUPPORTED; } else a1 = a0;
+  if (!make_w_map(&b, w, d->kh * d->kw * p.Ctot, Cout, BN)) return SEGSDE_E_UNSUPPORTED;
+  return BN == 128 ? launch_conv<128>(a0, a1, b, p, as_stream(stream)) : launch_conv<64>(a0, a1, b, p, as_stream(stream));
+}
+
+// dgrad on the tensor cores = fprop of dy with the transposed/tap-flipped weights; the Python layer prepares
+// those weights (segsde_weight_transpose_flip) and calls segsde_conv2d_fwd_tc, so this entry only reports
+// that the direct form is not offered.
+extern "C" int segsde_conv2d_dgrad_tc(const segsde_nhwc_t*, const float*, const segsde_nhwc_t*, const segsde_nhwc_t*,
+                                      const segsde_conv_desc_t*, void*) {
+  return SEGSDE_E_UNSUPPORTED;
+}
+
+extern "C" int segsde_conv2d_wgrad_tc(const segsde_nhwc_t* x1, const segsde_nhwc_t* x2, const segsde_nhwc_t* dy,
+                                      float* dw, float* dbias, const segsde_conv_desc_t* d, void* stream) {
+  if (!x1 || !x1->ptr || !dy || !dy->ptr || !dw || !d) return SEGSDE_E_ARG;
+  if (!tc_init()) return SEGSDE_E_UNSUPPORTED;
+  if (dbias) return SEGSDE_E_UNSUPPORTED;      // bias gradient is produced by segsde_act_bwd_bias
+  if (d->pad_mode != SEGSDE_PAD_ZERO || d->up1 || d->nchw_norm_in || d->stride != 1) return SEGSDE_E_UNSUPPORTED;
+  View v1 = mk(x1), v2 = mk(x2), vd = mk(dy);
+  const int C1 = v1.c, C2 = v2.p ? v2.c : 0, Cout = vd.c;
+  if (C1 % 32 || C2 % 32 || Cout % 32) return SEGSDE_E_UNSUPPORTED;
+  const int Ho = v1.h + 2 * d->pad - d->dil * (d->kh - 1), Wo = v1.w + 2 * d->pad - d->dil * (d->kw - 1);
+  if (vd.h != Ho || vd.w != Wo || vd.n != v1.n) return SEGSDE_E_ARG;
+  if (Wo % 32) return SEGSDE_E_UNSUPPORTED;
+  const int BN = (Cout % 128 == 0) ? 128 : (Cout % 64 == 0 ? 64 : 32);
+  TcWgradP p;
+  p.dw = dw; p.C[0] = C1; p.C[1] = C2; p.Ctot = C1 + C2; p.Cout = Cout; p.Ktot = d->kh * d->kw * p.Ctot;
+  p.kh = d->kh; p.kw = d->kw; p.pad = d->pad; p.dil = d->dil;
+  p.Ho = Ho; p.Wo = Wo; p.N = v1.n; p.wchunks = Wo / 32;
+  p.chunks = (long long)p.N * Ho * p.wchunks;
+  p.mtiles = cdiv(p.Ktot, 128); p.ntiles = Cout / BN;
+  long long want = (2LL * num_sms()) / ((long long)p.mtiles * p.ntiles);
+  if (want < 1) want = 1;
+  long long maxs = p.chunks / 16; if (maxs < 1) maxs = 1;
+  p.splits = (int)(want < maxs ? want : maxs);
+  p.chunks_per_split = (p.chunks + p.splits - 1) / p.splits;
+  p.splits = (int)((p.chunks + p.chunks_per_split - 1) / p.chunks_per_split);
+  CUtensorMap x0m, x1m, dym;
+  if (!make_act_map(&x0m, v1, 32, 1, 1)) return SEGSDE_E_UNSUPPORTED;
+  if (C2) { if (!make_act_map(&x1m, v2, 32, 1, 1)) return SEGSDE_E_UNSUPPORTED; } else x1m = x0m;
+  if (!make_act_map(&dym, vd, 32, 1, 1)) return SEGSDE_E_UNSUPPORTED;
+  cudaStream_t st = as_stream(stream);
+  if (BN == 128) return launch_wgrad<128>(x0m, x1m, dym, p, st);
+  if (BN == 64) return launch_wgrad<64>(x0m, x1m, dym, p, st);
+  return launch_wgrad<32>(x0m, x1m, dym, p, st);
+}

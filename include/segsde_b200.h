@@ -90,6 +90,18 @@ int segsde_conv2d_dgrad_tc(const segsde_nhwc_t* dy, const float* w, const segsde
 int segsde_conv2d_wgrad_tc(const segsde_nhwc_t* x1, const segsde_nhwc_t* x2,
                            const segsde_nhwc_t* dy, float* dw, float* dbias,
                            const segsde_conv_desc_t* d, void* stream);
+/* Helpers of the tensor-core route.
+ * pad_prep: y[N, Hc+2p, Wc+2p, C] = ReflectionPad2d(p)(nearest-x2-upsample?(x)), (Hc,Wc) = (H,W) << up;
+ * pad_fold: its adjoint (gradient w.r.t. x from the gradient w.r.t. the padded tensor);
+ * weight_transpose_flip: wt[ci-c_begin][kh-1-r][kw-1-s][co] = w[co][r][s][ci], which makes
+ *   dgrad(dy, w) == fprop(dy, wt) with pad' = dil*(k-1) - pad;
+ * act_bwd_bias: dz = dy * act'(y) (dz may be NULL) and dbias[c] += sum_pixels dz (dbias may be NULL). */
+int segsde_pad_prep(const segsde_nhwc_t* x, const segsde_nhwc_t* y, int up, int pad, void* stream);
+int segsde_pad_fold(const segsde_nhwc_t* dyp, const segsde_nhwc_t* dx, int up, int pad, void* stream);
+int segsde_weight_transpose_flip(const float* w, float* wt, int cout, int kh, int kw, int ctot, int c_begin,
+                                 int c_count, void* stream);
+int segsde_act_bwd_bias(const segsde_nhwc_t* y, const segsde_nhwc_t* dy, const segsde_nhwc_t* dz, int act,
+                        float* dbias, void* stream);
 /* 1 if this process can run the tensor-core path (driver entry point for tensor maps found). */
 int segsde_tc_available(void);
 

@@ -1,0 +1,85 @@
+"""GPU: the tcgen05/TMA implicit-GEMM convolution family against the generic CUDA-core kernels (same inputs,
+same C-ABI) and against PyTorch fp32 on the CPU.  TF32 operands (10-bit mantissa) with fp32 accumulation:
+tolerance 3e-3 relative to the output scale, the numerics class of the reference's own cuDNN path."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 3e-3
+
+
+def _mods():
+    from improving_segmentation_with_selfsupervised_depth_b200 import _cabi as A
+    from improving_segmentation_with_selfsupervised_depth_b200 import ops
+    return A, ops
+
+
+def _ref(x1, x2, w, b, pad, dil, reflect, up1, act):
+    x = F.interpolate(x1, scale_factor=2, mode="nearest") if up1 else x1
+    if x2 is not None:
+        x = torch.cat([x, x2], 1)
+    if reflect:
+        y = F.conv2d(F.pad(x, (pad,) * 4, mode="reflect"), w, b, 1, 0, dil)
+    else:
+        y = F.conv2d(x, w, b, 1, pad, dil)
+    return {0: lambda t: t, 1: F.relu, 2: F.elu, 3: torch.sigmoid}[act](y)
+
+
+CASES = [
+    # c1, c2, cout, k, pad, dil, reflect, up1, act, bias, N, H, W
+    (64, 0, 64, 1, 0, 1, False, False, 0, False, 2, 16, 32),
+    (64, 0, 128, 3, 1, 1, False, False, 1, False, 2, 16, 32),
+    (128, 0, 64, 3, 1, 1, False, False, 0, True, 1, 8, 128),
+    (32, 0, 64, 3, 2, 2, False, False, 0, False, 2, 12, 40),
+    (64, 0, 64, 3, 6, 6, False, False, 1, False, 2, 8, 16),
+    (64, 0, 64, 3, 1, 1, True, False, 2, True, 2, 16, 32),
+    (64, 32, 128, 3, 1, 1, True, True, 2, True, 2, 8, 16),
+    (64, 64, 64, 3, 1, 1, True, False, 2, True, 1, 32, 64),
+    (256, 0, 192, 1, 0, 1, False, False, 0, False, 2, 9, 13),
+    (96, 0, 256, 3, 1, 1, False, False, 0, False, 1, 20, 160),
+]
+
+
+def test_tc_is_available():
+    A, _ = _mods()
+    assert A.lib().segsde_tc_available() == 1
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_tc_conv_fwd_bwd(case):
+    A, ops = _mods()
+    ops.USE_TC = True
+    c1, c2, co, k, pad, dil, reflect, up1, act, bias, N, H, W = case
+    g = torch.Generator().manual_seed(abs(hash(case)) % 997)
+    x1 = torch.randn(N, c1, H, W, generator=g).requires_grad_()
+    H2, W2 = (2 * H, 2 * W) if up1 else (H, W)
+    x2 = torch.randn(N, c2, H2, W2, generator=g).requires_grad_() if c2 else None
+    w = (torch.randn(co, c1 + c2, k, k, generator=g) / ((c1 + c2) * k * k) ** 0.5).requires_grad_()
+    b = torch.randn(co, generator=g).requires_grad_() if bias else None
+    y = _ref(x1, x2, w, b, pad, dil, reflect, up1, act)
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy)
+    gx1 = x1.detach().cuda().requires_grad_()
+    gx2 = x2.detach().cuda().requires_grad_() if c2 else None
+    gw = w.detach().cuda().contiguous(memory_format=torch.channels_last).requires_grad_()
+    gb = b.detach().cuda().requires_grad_() if bias else None
+    n0 = A.launch_count()
+    ops.PROFILE = []
+    gy = ops.conv2d(gx1, gw, gb, x2=gx2, stride=1, pad=pad, dil=dil,
+                    pad_mode=A.PAD_REFLECT if reflect else A.PAD_ZERO, up1=up1, act=act)
+    gy.backward(dy.cuda())
+    torch.cuda.synchronize()
+    ops.PROFILE = None
+    assert gy.shape == y.shape
+    assert rel_err(gy, y) < TOL, "fprop"
+    assert rel_err(gx1.grad, x1.grad) < TOL, "dgrad x1"
+    if c2:
+        assert rel_err(gx2.grad, x2.grad) < TOL, "dgrad x2"
+    assert rel_err(gw.grad, w.grad) < TOL, "wgrad"
+    if bias:
+        assert rel_err(gb.grad, b.grad) < 1e-4, "dbias"
+    assert A.launch_count() > n0
