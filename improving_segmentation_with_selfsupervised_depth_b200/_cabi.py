@@ -67,17 +67,32 @@ def check(code, what=""):
         raise SegsdeError("%s failed (%d): %s" % (what, code, msg))
 
 
+# when a list, every entry-point call is bracketed by CUDA events: (name, ev0, ev1) — profiling scripts only
+PROFILE = None
+
+
+def _invoke(name, args):
+    fn = getattr(lib(), name)
+    if PROFILE is None:
+        return fn(*args)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    code = fn(*args)
+    e1.record()
+    PROFILE.append((name, e0, e1))
+    return code
+
+
 def call(name, *args):
     """Calls an int-returning entry point and raises on a non-zero code."""
-    fn = getattr(lib(), name)
-    code = fn(*args)
+    code = _invoke(name, args)
     if code != 0:
         check(code, name)
 
 
 def try_call(name, *args):
     """Like call() but returns False on SEGSDE_E_UNSUPPORTED (shape outside a kernel family)."""
-    code = getattr(lib(), name)(*args)
+    code = _invoke(name, args)
     if code == E_UNSUPPORTED:
         return False
     if code != 0:

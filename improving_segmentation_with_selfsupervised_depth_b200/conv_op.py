@@ -29,7 +29,7 @@ def _prep(x, up, pad):
     return y
 
 
-def _fwd(x1, x2, w, b, y, d, kind, flops):
+def _fwd(x1, x2, w, b, y, d, kind, flops, desc=None):
     st = A.stream_ptr()
     v1, v2, vy = ops.view(x1), (ops.view(x2) if x2 is not None else None), ops.view(y)
     if d.nchw_norm_in:
@@ -40,7 +40,7 @@ def _fwd(x1, x2, w, b, y, d, kind, flops):
                                         C.byref(vy), C.byref(d), st):
             return
         A.call("segsde_conv2d_fwd", C.byref(v1), ops._ref(v2), A.ptr(w), A.ptr(b), C.byref(vy), C.byref(d), st)
-    ops._timed(kind, flops, launch)
+    ops._timed(kind, flops, launch, desc)
 
 
 class _Conv2dFn(torch.autograd.Function):
@@ -71,10 +71,12 @@ class _Conv2dFn(torch.autograd.Function):
         y = ops.cl_empty(n, cout, ho, wo, x1.device)
         d = ops._desc(kh, kw, stride, pad_e, dil, mode_e, up_e, act, nchw)
         b = bias.detach() if bias is not None else None
-        _fwd(x1e, x2e, w, b, y, d, "fprop", 2.0 * n * ho * wo * cout * kh * kw * ctot)
+        desc = "%d+%d->%d k%d s%d d%d out %dx%d%s" % (c1, c2, cout, kh, stride, dil, ho, wo, " prep" if prepped else "")
+        _fwd(x1e, x2e, w, b, y, d, "fprop", 2.0 * n * ho * wo * cout * kh * kw * ctot, desc)
         ctx.save_for_backward(x1e, x2e, w, y if act != A.ACT_NONE else None)
         ctx.cfg = (stride, pad, dil, pad_mode, up1, act, nchw, bias is not None, prepped, pad_e, mode_e, up_e,
                    tuple(x1.shape), tuple(x2.shape) if x2 is not None else None)
+        ctx.desc = desc
         return y
 
     @staticmethod
@@ -116,7 +118,7 @@ class _Conv2dFn(torch.autograd.Function):
                            C.c_int(ctot), C.c_int(c0), C.c_int(cn), st)
                     gx = ops.cl_empty(*xe.shape, dev)
                     dd = ops._desc(kh, kw, 1, dil * (kh - 1) - pad_e, dil, A.PAD_ZERO, False, A.ACT_NONE, False)
-                    _fwd(dz, None, wt, None, gx, dd, "dgrad", 2.0 * n * ho * wo * cout * kh * kw * cn)
+                    _fwd(dz, None, wt, None, gx, dd, "dgrad", 2.0 * n * ho * wo * cout * kh * kw * cn, ctx.desc)
                     results.append(gx)
                 else:
                     results.append("generic")
@@ -129,7 +131,7 @@ class _Conv2dFn(torch.autograd.Function):
                 cneed = (c1 if g1 is not None else 0) + (c2 if g2 is not None else 0)
                 ops._timed("dgrad", 2.0 * n * ho * wo * cout * kh * kw * cneed,
                            lambda: A.call("segsde_conv2d_dgrad", C.byref(ops.view(dz)), A.ptr(w), C.byref(v1),
-                                          ops._ref(v2), C.byref(d), st))
+                                          ops._ref(v2), C.byref(d), st), ctx.desc + " generic")
                 if g1 is not None:
                     results[0] = g1
                 if g2 is not None:
@@ -159,7 +161,7 @@ class _Conv2dFn(torch.autograd.Function):
                                                              C.byref(vdz), A.ptr(dw), None, C.byref(d), st):
                     return
                 A.call("segsde_conv2d_wgrad", C.byref(v1), ops._ref(v2), C.byref(vdz), A.ptr(dw), None, C.byref(d), st)
-            ops._timed("wgrad", 2.0 * n * ho * wo * cout * kh * kw * ctot, launch_w)
+            ops._timed("wgrad", 2.0 * n * ho * wo * cout * kh * kw * ctot, launch_w, ctx.desc)
         return dx1, dx2, dw, db, None, None, None, None, None, None, None
 
 

@@ -84,9 +84,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 }
 
 // shared-memory matrix descriptor, SWIZZLE_128B (cute::UMMA::SmemDescriptor: version 1, layout type 2)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout_type: 2 = SWIZZLE_128B (16-byte swizzle atoms, 8-row period; K-major operands),
+//              1 = SWIZZLE_128B_BASE32B (32-byte atoms, 4-row period) - the only layout tcgen05 accepts for
+//                  MN-major tf32 operands (cutlass sm100_common.inl:92)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type = 2) {
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | ((uint64_t)layout_type << 61);
 }
 // instruction descriptor for kind::tf32, fp32 accumulate, M = 128
 __host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major, int b_mn_major) {
@@ -334,8 +338,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant_
       if (lane == 0) {
         const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES), sb = sa + A_BYTES;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {     // 8 pixels (= one 8-row swizzle group, 1024 B) per MMA
-          const uint64_t ad = make_desc(sa + 1024 * k, 4096, 1024), bd = make_desc(sb + 1024 * k, 4096, 1024);
+        for (int k = 0; k < 4; ++k) {     // 8 pixels per MMA = two 4-row (512 B) BASE32B swizzle atoms along K
+          const uint64_t ad = make_desc(sa + 1024 * k, 4096, 512, 1), bd = make_desc(sb + 1024 * k, 4096, 512, 1);
           tc_mma_tf32(tmem_base, ad, bd, idesc, (it | k) != 0);
         }
         tc_commit(empty0 + 8 * stage);
@@ -392,7 +396,8 @@ static bool tc_init() {
 }
 
 // NHWC activation view -> 4-D map (C, W, H, N), box (32, bw, bh, 1), optional element stride on W/H
-static bool make_act_map(CUtensorMap* m, const View& v, int bw, int bh, int estride) {
+static bool make_act_map(CUtensorMap* m, const View& v, int bw, int bh, int estride,
+                         CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   if ((reinterpret_cast<uintptr_t>(v.p) & 15) || (v.sw % 4) || (v.sh % 4) || (v.sn % 4) || (v.c % 4)) return false;
   cuuint64_t dims[4] = {(cuuint64_t)v.c, (cuuint64_t)v.w, (cuuint64_t)v.h, (cuuint64_t)v.n};
   cuuint64_t strides[3] = {(cuuint64_t)v.sw * 4, (cuuint64_t)v.sh * 4, (cuuint64_t)v.sn * 4};
@@ -400,7 +405,7 @@ static bool make_act_map(CUtensorMap* m, const View& v, int bw, int bh, int estr
   cuuint32_t es[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
   if (box[1] > 256 || box[2] > 256) return false;
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, v.p, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 static bool make_w_map(CUtensorMap* m, const float* w, int ktot, int cout, int bn) {
@@ -514,9 +519,10 @@ extern "C" int segsde_conv2d_wgrad_tc(const segsde_nhwc_t* x1, const segsde_nhwc
   p.chunks_per_split = (p.chunks + p.splits - 1) / p.splits;
   p.splits = (int)((p.chunks + p.chunks_per_split - 1) / p.chunks_per_split);
   CUtensorMap x0m, x1m, dym;
-  if (!make_act_map(&x0m, v1, 32, 1, 1)) return SEGSDE_E_UNSUPPORTED;
-  if (C2) { if (!make_act_map(&x1m, v2, 32, 1, 1)) return SEGSDE_E_UNSUPPORTED; } else x1m = x0m;
-  if (!make_act_map(&dym, vd, 32, 1, 1)) return SEGSDE_E_UNSUPPORTED;
+  const CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  if (!make_act_map(&x0m, v1, 32, 1, 1, swz)) return SEGSDE_E_UNSUPPORTED;
+  if (C2) { if (!make_act_map(&x1m, v2, 32, 1, 1, swz)) return SEGSDE_E_UNSUPPORTED; } else x1m = x0m;
+  if (!make_act_map(&dym, vd, 32, 1, 1, swz)) return SEGSDE_E_UNSUPPORTED;
   cudaStream_t st = as_stream(stream);
   if (BN == 128) return launch_wgrad<128>(x0m, x1m, dym, p, st);
   if (BN == 64) return launch_wgrad<64>(x0m, x1m, dym, p, st);

@@ -19,7 +19,10 @@ USE_TC = True
 PROFILE = None
 
 
-def _timed(kind, flops, fn):
+PROFILE_DESC = None   # optional parallel list of human-readable shapes (profiling scripts)
+
+
+def _timed(kind, flops, fn, desc=None):
     if PROFILE is None:
         return fn()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -27,6 +30,8 @@ def _timed(kind, flops, fn):
     r = fn()
     e1.record()
     PROFILE.append((kind, flops, e0, e1))
+    if PROFILE_DESC is not None:
+        PROFILE_DESC.append(desc)
     return r
 
 

@@ -160,3 +160,54 @@ def test_frozen_encoder_and_eval_mode(contracts):
         ref = O.model_forward(cpu_sd, cin, cfg, O.BNMode(False))
     for s in range(4):
         assert rel_err(ev[("disp", s)], ref[("disp", s)]) < 2e-4
+
+
+def test_model_tensor_core_path_vs_oracle(contracts):
+    """The network through the tcgen05 route (TF32 operands, fp32 accumulate).  Eval-mode BatchNorm keeps the
+    comparison well conditioned (train-mode statistics over the 2-sample ASPP pooling branch amplify TF32
+    rounding by 1/sqrt(var+eps), see test_network_gradients_vs_oracle).  Features are compared in relative L2
+    (1e-2), disparities absolutely (they saturate towards 0 with synthetic weights), parameter gradients of a
+    smooth surrogate loss on the decoder features in relative L2 (5e-2)."""
+    from improving_segmentation_with_selfsupervised_depth_b200 import ops
+    name, (H, W), B = "mono_r50", (64, 96), 2
+    model, sd = build(contracts, name, H, W, use_tc=True)
+
+    def l2(a, b):
+        a, b = a.detach().double().cpu(), b.detach().double().cpu()
+        return ((a - b).norm() / (b.norm() + 1e-30)).item()
+    try:
+        model.eval()
+        inputs = O.synthetic_inputs(B, H, W, seed=5)
+        g = torch.Generator().manual_seed(78)
+        osd = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in sd.items()}
+        cfg = {"num_layers": 50, "rswd": [False, False, True], "frame_ids": [0, -1, 1]}
+        ref = O.model_forward(osd, inputs, cfg, O.BNMode(False))
+        wu = [torch.randn(ref[("upconv", i)].shape, generator=g) for i in range(5)]
+        rl = sum((ref[("upconv", i)] * wu[i]).mean() for i in range(5)) + 100 * ref[("cam_T_cam", 0, 1)].sum()
+        rl.backward()
+        gin = {k: v.cuda() for k, v in inputs.items()}
+        ops.PROFILE = []
+        with contextlib.redirect_stdout(io.StringIO()):
+            out = model(gin)
+        assert "fprop" in {k for k, *_ in ops.PROFILE}
+        feats = model.models["encoder"].features
+        for i in range(5):
+            assert l2(feats[i], ref["features"][i]) < 1e-2, ("feature", i)
+            assert l2(out[("upconv", i)], ref[("upconv", i)]) < 1e-2, ("upconv", i)
+        for s in range(4):
+            assert (out[("disp", s)].cpu() - ref[("disp", s)]).abs().max().item() < 5e-3, s
+        assert rel_err(out[("cam_T_cam", 0, 1)], ref[("cam_T_cam", 0, 1)]) < 1e-3
+        gl = sum((out[("upconv", i)] * wu[i].cuda()).mean() for i in range(5)) + 100 * out[("cam_T_cam", 0, 1)].sum()
+        gl.backward()
+        bad = []
+        for n, q in model.named_parameters():
+            r = osd[n].grad
+            if r is None or r.norm().item() == 0:
+                continue
+            e = l2(q.grad, r)
+            if e > 5e-2:
+                bad.append((n, e))
+        assert not bad, bad[:8]
+    finally:
+        ops.PROFILE = None
+        ops.USE_TC = False
