@@ -35,7 +35,7 @@ class ReprojArgs(C.Structure):
                 ("ws", C.c_int32), ("F", C.c_int32), ("min_depth", C.c_float),
                 ("max_depth", C.c_float), ("flags", C.c_int32),
                 ("loss_partial", C.c_void_p), ("ident_sel", C.c_void_p), ("gdisp", C.c_void_p),
-                ("gT_partial", C.c_void_p)]
+                ("gT_partial", C.c_void_p), ("ident_cache", C.c_void_p), ("ident_mode", C.c_int32)]
 
 
 ACT_NONE, ACT_RELU, ACT_ELU, ACT_SIGMOID = 0, 1, 2, 3

@@ -1,12 +1,17 @@
 """Convolution autograd op: routes every eligible conv to the tcgen05/TMA kernels (conv_tc.cu) and the
-rest (3/6-channel stem, C->1 disparity heads, 12-channel pose output, stride 2) to the generic CUDA-core
-kernels (conv_simt.cu).
+rest (3/6-channel stem, C->1 disparity heads, 12-channel pose output) to the generic CUDA-core kernels
+(conv_simt.cu / conv_small.cu).
 
-Tensor-core route for the decoder's fused inputs: reflection padding and nearest x2 upsampling are
-materialised once into a halo-padded NHWC buffer (`segsde_pad_prep`), after which the convolution is a
-plain "valid" one whose taps are TMA boxes at shifted coordinates; the concat stays virtual (second
-tensor map).  Backward: dgrad = the same fprop kernel on dy with the transposed / tap-flipped weights, the
-halo buffer's gradient is folded back with `segsde_pad_fold`, wgrad reads the saved padded buffers.
+Tensor-core route, by input-side fusion:
+  * reflection padding / nearest x2 upsampling (decoder): materialised once into a halo-padded NHWC buffer
+    (`segsde_pad_prep`), after which the conv is a plain "valid" one whose taps are TMA boxes at shifted
+    coordinates; the concat stays virtual (second tensor map).  The halo buffer's gradient is folded back with
+    `segsde_pad_fold`; wgrad reads the saved padded buffers.
+  * stride 2, 1x1 (ResNet downsample): a stride-1 conv on the ::2 strided view (the TMA map just gets doubled
+    pixel strides); its dgrad writes through the same strided view of a zero-filled gradient.
+  * stride 2, 3x3: fprop through TMA element strides; for dgrad/wgrad the output gradient is zero-stuffed to
+    the stride-1 output grid, which turns both into the stride-1 kernels.
+  * dgrad everywhere = the fprop kernel on dy with the transposed / tap-flipped weights.
 """
 import ctypes as C
 
@@ -14,6 +19,8 @@ import torch
 
 from . import _cabi as A
 from . import ops
+
+TC_STRIDE2_FPROP = True      # 3x3/s2 forward on the tensor cores via TMA element strides
 
 
 def _tc_enabled():
@@ -55,13 +62,19 @@ class _Conv2dFn(torch.autograd.Function):
             x2 = ops.as_cl(x2) if x2 is not None else None
         w = ops.ohwi(weight.detach())
         cout, ctot, kh, kw = w.shape
-        n, c1, h1, w1 = x1.shape
+        full_shape1 = tuple(x1.shape)
+        c1 = x1.shape[1]
         c2 = x2.shape[1] if x2 is not None else 0
+        tc_ch = (not nchw and c1 % 32 == 0 and c2 % 32 == 0 and cout % 64 == 0 and _tc_enabled())
+        sub2 = False
+        if stride == 2 and kh == 1 and kw == 1 and pad == 0 and x2 is None and tc_ch:
+            x1 = x1[:, :, ::2, ::2]          # 1x1 / stride 2 == 1x1 / stride 1 on the subsampled view
+            stride, sub2 = 1, True
+        n, _, h1, w1 = x1.shape
         hc, wc = (h1 * 2, w1 * 2) if up1 else (h1, w1)
         ho, wo = ops._conv_out_hw(hc, wc, kh, kw, stride, pad, dil)
         reflect = pad_mode == A.PAD_REFLECT
-        tc_shape = (not nchw and stride == 1 and c1 % 32 == 0 and c2 % 32 == 0 and cout % 64 == 0 and _tc_enabled())
-        prepped = tc_shape and (reflect or up1) and pad > 0
+        prepped = tc_ch and stride == 1 and (reflect or up1) and pad > 0
         if prepped:          # materialise padding (+ upsampling); the conv becomes a plain valid one
             x1e = _prep(x1, up1, pad)
             x2e = _prep(x2, False, pad) if x2 is not None else None
@@ -71,18 +84,20 @@ class _Conv2dFn(torch.autograd.Function):
         y = ops.cl_empty(n, cout, ho, wo, x1.device)
         d = ops._desc(kh, kw, stride, pad_e, dil, mode_e, up_e, act, nchw)
         b = bias.detach() if bias is not None else None
-        desc = "%d+%d->%d k%d s%d d%d out %dx%d%s" % (c1, c2, cout, kh, stride, dil, ho, wo, " prep" if prepped else "")
+        desc = "%d+%d->%d k%d s%d d%d out %dx%d%s%s" % (c1, c2, cout, kh, stride, dil, ho, wo,
+                                                        " prep" if prepped else "", " sub2" if sub2 else "")
         _fwd(x1e, x2e, w, b, y, d, "fprop", 2.0 * n * ho * wo * cout * kh * kw * ctot, desc)
         ctx.save_for_backward(x1e, x2e, w, y if act != A.ACT_NONE else None)
         ctx.cfg = (stride, pad, dil, pad_mode, up1, act, nchw, bias is not None, prepped, pad_e, mode_e, up_e,
-                   tuple(x1.shape), tuple(x2.shape) if x2 is not None else None)
+                   tuple(x1.shape), tuple(x2.shape) if x2 is not None else None, sub2, full_shape1, tc_ch)
         ctx.desc = desc
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x1e, x2e, w, y = ctx.saved_tensors
-        (stride, pad, dil, pad_mode, up1, act, nchw, has_bias, prepped, pad_e, mode_e, up_e, shp1, shp2) = ctx.cfg
+        (stride, pad, dil, pad_mode, up1, act, nchw, has_bias, prepped, pad_e, mode_e, up_e, shp1, shp2, sub2,
+         full_shape1, tc_ch) = ctx.cfg
         cout, ctot, kh, kw = w.shape
         st = A.stream_ptr()
         dy = ops.as_cl(dy)
@@ -100,6 +115,15 @@ class _Conv2dFn(torch.autograd.Function):
         n, _, ho, wo = dz.shape
         c1 = x1e.shape[1]
         c2 = x2e.shape[1] if x2e is not None else 0
+        flops_scale = 1.0
+        if stride == 2 and tc_ch and mode_e == A.PAD_ZERO and not up_e and not nchw and (need1 or need2 or needw):
+            # zero-stuff dz onto the stride-1 output grid: dgrad and wgrad become stride-1 problems
+            hs = x1e.shape[2] + 2 * pad_e - dil * (kh - 1)
+            ws = x1e.shape[3] + 2 * pad_e - dil * (kw - 1)
+            dzu = ops.cl_empty(n, cout, hs, ws, dev, zero=True)
+            A.call("segsde_copy_nhwc", C.byref(ops.view(dz)), C.byref(ops.view(dzu[:, :, ::2, ::2][:, :, :ho, :wo])), st)
+            dz, stride, flops_scale = dzu, 1, 0.25        # algorithmic flops stay those of the strided conv
+        nz, _, hz, wz = dz.shape
         d = ops._desc(kh, kw, stride, pad_e, dil, mode_e, up_e, A.ACT_NONE, nchw)
         dx1 = dx2 = dw = None
 
@@ -108,7 +132,8 @@ class _Conv2dFn(torch.autograd.Function):
             tc_dgrad = (_tc_enabled() and stride == 1 and mode_e == A.PAD_ZERO and not up_e and cout % 32 == 0
                         and dil * (kh - 1) - pad_e >= 0)
             results = []
-            for need, xe, c0, cn in ((need1, x1e, 0, c1), (need2 and x2e is not None, x2e, c1, c2)):
+            full1 = None
+            for idx, (need, xe, c0, cn) in enumerate(((need1, x1e, 0, c1), (need2 and x2e is not None, x2e, c1, c2))):
                 if not need:
                     results.append(None)
                     continue
@@ -116,9 +141,13 @@ class _Conv2dFn(torch.autograd.Function):
                     wt = torch.empty(cn * kh * kw * cout, device=dev, dtype=torch.float32)
                     A.call("segsde_weight_transpose_flip", A.ptr(w), A.ptr(wt), C.c_int(cout), C.c_int(kh), C.c_int(kw),
                            C.c_int(ctot), C.c_int(c0), C.c_int(cn), st)
-                    gx = ops.cl_empty(*xe.shape, dev)
+                    if sub2 and idx == 0:      # gradient of the ::2 view: written through the view, zeros elsewhere
+                        full1 = ops.cl_empty(*full_shape1, dev, zero=True)
+                        gx = full1[:, :, ::2, ::2]
+                    else:
+                        gx = ops.cl_empty(*xe.shape, dev)
                     dd = ops._desc(kh, kw, 1, dil * (kh - 1) - pad_e, dil, A.PAD_ZERO, False, A.ACT_NONE, False)
-                    _fwd(dz, None, wt, None, gx, dd, "dgrad", 2.0 * n * ho * wo * cout * kh * kw * cn, ctx.desc)
+                    _fwd(dz, None, wt, None, gx, dd, "dgrad", flops_scale * 2.0 * nz * hz * wz * cout * kh * kw * cn, ctx.desc)
                     results.append(gx)
                 else:
                     results.append("generic")
@@ -129,14 +158,19 @@ class _Conv2dFn(torch.autograd.Function):
                 v1 = ops.view(g1) if g1 is not None else ops.view(x1e, null=True)
                 v2 = (ops.view(g2) if g2 is not None else ops.view(x2e, null=True)) if x2e is not None else None
                 cneed = (c1 if g1 is not None else 0) + (c2 if g2 is not None else 0)
-                ops._timed("dgrad", 2.0 * n * ho * wo * cout * kh * kw * cneed,
+                ops._timed("dgrad", flops_scale * 2.0 * nz * hz * wz * cout * kh * kw * cneed,
                            lambda: A.call("segsde_conv2d_dgrad", C.byref(ops.view(dz)), A.ptr(w), C.byref(v1),
                                           ops._ref(v2), C.byref(d), st), ctx.desc + " generic")
                 if g1 is not None:
                     results[0] = g1
+                    if sub2:
+                        full1 = ops.cl_empty(*full_shape1, dev, zero=True)
+                        A.call("segsde_copy_nhwc", C.byref(ops.view(g1)), C.byref(ops.view(full1[:, :, ::2, ::2])), st)
                 if g2 is not None:
                     results[1] = g2
             dx1, dx2 = results[0], results[1]
+            if sub2 and dx1 is not None:
+                dx1 = full1
             if prepped:          # fold the halo / upsampling back onto the original tensors
                 if dx1 is not None:
                     f = ops.cl_empty(*shp1, dev)
@@ -148,7 +182,7 @@ class _Conv2dFn(torch.autograd.Function):
                     A.call("segsde_pad_fold", C.byref(ops.view(dx2)), C.byref(ops.view(f)), C.c_int(0), C.c_int(pad), st)
                     dx2 = f
 
-        # ---- wgrad (+ bias gradient on the generic path) ------------------------------------------------
+        # ---- wgrad --------------------------------------------------------------------------------------
         if needw:
             dw = torch.zeros_like(w)
             v1, v2 = ops.view(x1e), (ops.view(x2e) if x2e is not None else None)
@@ -161,11 +195,68 @@ class _Conv2dFn(torch.autograd.Function):
                                                              C.byref(vdz), A.ptr(dw), None, C.byref(d), st):
                     return
                 A.call("segsde_conv2d_wgrad", C.byref(v1), ops._ref(v2), C.byref(vdz), A.ptr(dw), None, C.byref(d), st)
-            ops._timed("wgrad", 2.0 * n * ho * wo * cout * kh * kw * ctot, launch_w, ctx.desc)
+            ops._timed("wgrad", flops_scale * 2.0 * nz * hz * wz * cout * kh * kw * ctot, launch_w, ctx.desc)
         return dx1, dx2, dw, db, None, None, None, None, None, None, None
+
+
+class _StemConvFn(torch.autograd.Function):
+    """7x7/s2 stem on NCHW frames (resnet_encoder.py:92-93) as im2col + tensor-core 1x1 GEMM; the input
+    normalisation (x-0.45)/0.225 happens inside the im2col pass.  Only the weight gets a gradient."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, weight, stride, pad):
+        A.require_cuda(x1, weight)
+        x1 = x1.contiguous().float()
+        x2 = x2.contiguous().float() if x2 is not None else None
+        w = ops.ohwi(weight.detach())
+        cout, ctot, kh, kw = w.shape
+        n, c1, h, wd = x1.shape
+        c2 = x2.shape[1] if x2 is not None else 0
+        k = kh * kw * ctot
+        kpad = (k + 31) // 32 * 32
+        ho, wo = ops._conv_out_hw(h, wd, kh, kw, stride, pad, 1)
+        st = A.stream_ptr()
+        cols = ops.cl_empty(n, kpad, ho, wo, x1.device)
+        A.call("segsde_stem_im2col", A.ptr(x1), A.ptr(x2), C.c_int(c1), C.c_int(c2), C.c_int(n), C.c_int(h), C.c_int(wd),
+               C.c_int(kh), C.c_int(kw), C.c_int(stride), C.c_int(pad), C.c_int(kpad), A.ptr(cols), st)
+        wpad = torch.empty(cout * kpad, device=x1.device, dtype=torch.float32)
+        A.call("segsde_copy_rows", A.ptr(w), C.c_int(k), A.ptr(wpad), C.c_int(kpad), C.c_int(cout), C.c_int(k), st)
+        y = ops.cl_empty(n, cout, ho, wo, x1.device)
+        d = ops._desc(1, 1, 1, 0, 1, A.PAD_ZERO, False, A.ACT_NONE, False)
+        desc = "stem %d+%d->%d k%d s%d out %dx%d im2col" % (c1, c2, cout, kh, stride, ho, wo)
+        _fwd(cols, None, wpad, None, y, d, "fprop", 2.0 * n * ho * wo * cout * k, desc)
+        ctx.save_for_backward(cols, w)
+        ctx.cfg = (k, kpad, desc)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        cols, w = ctx.saved_tensors
+        k, kpad, desc = ctx.cfg
+        if not ctx.needs_input_grad[2]:
+            return None, None, None, None, None
+        cout = w.shape[0]
+        dy = ops.as_cl(dy)
+        st = A.stream_ptr()
+        n, _, ho, wo = dy.shape
+        dwp = torch.zeros(cout * kpad, device=dy.device, dtype=torch.float32)
+        d = ops._desc(1, 1, 1, 0, 1, A.PAD_ZERO, False, A.ACT_NONE, False)
+        v1, vdz = ops.view(cols), ops.view(dy)
+
+        def launch_w():
+            if A.try_call("segsde_conv2d_wgrad_tc", C.byref(v1), None, C.byref(vdz), A.ptr(dwp), None, C.byref(d), st):
+                return
+            A.call("segsde_conv2d_wgrad", C.byref(v1), None, C.byref(vdz), A.ptr(dwp), None, C.byref(d), st)
+        ops._timed("wgrad", 2.0 * n * ho * wo * cout * k, launch_w, desc)
+        dw = torch.empty_like(w)
+        A.call("segsde_copy_rows", A.ptr(dwp), C.c_int(kpad), A.ptr(dw), C.c_int(k), C.c_int(cout), C.c_int(k), st)
+        return None, None, dw, None, None
 
 
 def conv2d(x1, weight, bias=None, x2=None, stride=1, pad=0, dil=1, pad_mode=A.PAD_ZERO, up1=False,
            act=A.ACT_NONE, nchw_norm_in=False):
     """y = act(conv(cat(up?(x1), x2)) + bias) — see segsde_conv2d_fwd / segsde_conv2d_fwd_tc."""
+    if (nchw_norm_in and bias is None and act == A.ACT_NONE and dil == 1 and weight.shape[0] % 64 == 0
+            and _tc_enabled()):
+        return _StemConvFn.apply(x1, x2, weight, stride, pad)
     return _Conv2dFn.apply(x1, x2, weight, bias, stride, pad, dil, pad_mode, up1, act, nchw_norm_in)

@@ -1,0 +1,231 @@
+// Bandwidth-tuned BatchNorm / activation-backward kernels for pixel-contiguous NHWC tensors
+// (offset(pixel, c) = pixel*ld + c): no per-element div/mod, float4 channel vectors, fp32 partial sums around a
+// per-channel shift (the value at pixel 0) so that E[(x-s)^2] - E[x-s]^2 does not cancel, fp64 across threads.
+// The generic strided kernels in elementwise.cu remain the path for strided views and tiny tensors.
+#include "common.cuh"
+
+namespace segsde {
+
+bool pix_contig(const View& v) {
+  return v.p && v.sh == (long long)v.w * v.sw && v.sn == (long long)v.h * v.sh && vec4_ok(v);
+}
+
+struct Rows { float* p; long long ld; };
+static inline Rows rows_of(const View& v) { Rows r; r.p = v.p; r.ld = v.sw; return r; }
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
+
+// Column reductions.  block (32, 8); each warp row covers `ppw` pixels x `cq_w` float4 chunks.
+// MODE 0: S1 = sum (x - s), S2 = sum (x - s)^2 with s = x[pixel 0]; out[2C..3C) = s
+// MODE 1: S1 = sum dz, S2 = sum dz * xhat
+// MODE 2: dz = dy * act'(y) written out, S1 = sum dz (bias gradient, fp32 atomics into dbias)
+template <int MODE>
+__global__ void __launch_bounds__(256) colreduce_fast_kernel(Rows x, Rows y, Rows dy, Rows dz, long long P, int C,
+                                                             const float* __restrict__ mean,
+                                                             const float* __restrict__ invstd, int act,
+                                                             double* __restrict__ out, float* __restrict__ dbias,
+                                                             long long slab) {
+  const int cq = C >> 2;
+  const int cq_w = cq < 32 ? cq : 32;              // chunks per warp row
+  const int ppw = 32 / cq_w;                        // pixels per warp row
+  const int sub = threadIdx.x / cq_w;
+  const int c4 = blockIdx.y * 32 + (threadIdx.x % cq_w);
+  const bool cv = c4 < cq;
+  const int c = c4 * 4;
+  const long long pbeg = (long long)blockIdx.x * slab, pend = min(P, pbeg + slab);
+  float4 sh = make_float4(0.f, 0.f, 0.f, 0.f), mu = sh, is = sh;
+  if (cv) {
+    if (MODE == 0) sh = ld4(x.p + c);
+    if (MODE == 1) { mu = ld4(mean + c); is = ld4(invstd + c); }
+  }
+  double d1[4] = {0, 0, 0, 0}, d2[4] = {0, 0, 0, 0};
+  float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), a2 = a1;
+  int cnt = 0;
+  if (cv) {
+    for (long long p = pbeg + threadIdx.y * ppw + sub; p < pend; p += 8 * ppw) {
+      if (MODE == 0) {
+        const float4 v = ld4(x.p + p * x.ld + c);
+        const float e0 = v.x - sh.x, e1 = v.y - sh.y, e2 = v.z - sh.z, e3 = v.w - sh.w;
+        a1.x += e0; a1.y += e1; a1.z += e2; a1.w += e3;
+        a2.x = fmaf(e0, e0, a2.x); a2.y = fmaf(e1, e1, a2.y); a2.z = fmaf(e2, e2, a2.z); a2.w = fmaf(e3, e3, a2.w);
+      } else if (MODE == 1) {
+        float4 g = ld4(dy.p + p * dy.ld + c);
+        const float4 v = ld4(x.p + p * x.ld + c);
+        if (act == SEGSDE_ACT_RELU) {
+          const float4 o = ld4(y.p + p * y.ld + c);
+          g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f; g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
+        }
+        a1.x += g.x; a1.y += g.y; a1.z += g.z; a1.w += g.w;
+        a2.x = fmaf(g.x, (v.x - mu.x) * is.x, a2.x); a2.y = fmaf(g.y, (v.y - mu.y) * is.y, a2.y);
+        a2.z = fmaf(g.z, (v.z - mu.z) * is.z, a2.z); a2.w = fmaf(g.w, (v.w - mu.w) * is.w, a2.w);
+      } else {
+        float4 g = ld4(dy.p + p * dy.ld + c);
+        if (act != SEGSDE_ACT_NONE) {
+          const float4 o = ld4(y.p + p * y.ld + c);
+          g.x *= act_grad_from_out(o.x, act); g.y *= act_grad_from_out(o.y, act);
+          g.z *= act_grad_from_out(o.z, act); g.w *= act_grad_from_out(o.w, act);
+        }
+        if (dz.p) st4(dz.p + p * dz.ld + c, g);
+        a1.x += g.x; a1.y += g.y; a1.z += g.z; a1.w += g.w;
+      }
+      if (++cnt == 128) {       // bounded fp32 partials
+        d1[0] += a1.x; d1[1] += a1.y; d1[2] += a1.z; d1[3] += a1.w;
+        d2[0] += a2.x; d2[1] += a2.y; d2[2] += a2.z; d2[3] += a2.w;
+        a1 = make_float4(0.f, 0.f, 0.f, 0.f); a2 = a1; cnt = 0;
+      }
+    }
+    d1[0] += a1.x; d1[1] += a1.y; d1[2] += a1.z; d1[3] += a1.w;
+    d2[0] += a2.x; d2[1] += a2.y; d2[2] += a2.z; d2[3] += a2.w;
+  }
+  __shared__ double red[8][32][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { red[threadIdx.y][threadIdx.x][i] = d1[i]; red[threadIdx.y][threadIdx.x][4 + i] = d2[i]; }
+  __syncthreads();
+  if (threadIdx.y == 0 && sub == 0 && cv) {
+    double t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int yy = 0; yy < 8; ++yy)
+      for (int s = 0; s < ppw; ++s)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i] += red[yy][s * cq_w + (threadIdx.x % cq_w)][i];
+    if (MODE == 2) {
+      if (dbias)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) atomicAdd(dbias + c + i, (float)t[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { atomicAdd(out + c + i, t[i]); atomicAdd(out + C + c + i, t[4 + i]); }
+      if (MODE == 0 && blockIdx.x == 0) {
+        out[2 * C + c + 0] = sh.x; out[2 * C + c + 1] = sh.y; out[2 * C + c + 2] = sh.z; out[2 * C + c + 3] = sh.w;
+      }
+    }
+  }
+}
+
+// y = act((x - mean) * invstd * gamma + beta [+ res])
+__global__ void __launch_bounds__(256) bn_apply_fast_kernel(Rows x, Rows res, Rows y, long long total4, int cq, int cq_shift,
+                                                            const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            int act) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    long long p; int c4;
+    if (cq_shift >= 0) { p = i >> cq_shift; c4 = (int)(i & (cq - 1)); } else { p = i / cq; c4 = (int)(i - p * cq); }
+    const int c = c4 * 4;
+    const float4 v = ld4(x.p + p * x.ld + c);
+    const float4 m = ld4(mean + c), is = ld4(invstd + c);
+    const float4 g = gamma ? ld4(gamma + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float4 b = beta ? ld4(beta + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 o;
+    o.x = (v.x - m.x) * (is.x * g.x) + b.x; o.y = (v.y - m.y) * (is.y * g.y) + b.y;
+    o.z = (v.z - m.z) * (is.z * g.z) + b.z; o.w = (v.w - m.w) * (is.w * g.w) + b.w;
+    if (res.p) { const float4 r = ld4(res.p + p * res.ld + c); o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
+    if (act == SEGSDE_ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    st4(y.p + p * y.ld + c, o);
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_fast_kernel(Rows x, Rows y, Rows dy, Rows dx, Rows dres, long long total4,
+                                                                int cq, int cq_shift, int C,
+                                                                const float* __restrict__ mean,
+                                                                const float* __restrict__ invstd,
+                                                                const float* __restrict__ gamma, int relu, int training,
+                                                                const double* __restrict__ red, float inv_count) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    long long p; int c4;
+    if (cq_shift >= 0) { p = i >> cq_shift; c4 = (int)(i & (cq - 1)); } else { p = i / cq; c4 = (int)(i - p * cq); }
+    const int c = c4 * 4;
+    float g[4], xv[4], o[4];
+    { const float4 t = ld4(dy.p + p * dy.ld + c); g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w; }
+    { const float4 t = ld4(x.p + p * x.ld + c); xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w; }
+    if (relu) {
+      const float4 t = ld4(y.p + p * y.ld + c);
+      if (!(t.x > 0.f)) g[0] = 0.f; if (!(t.y > 0.f)) g[1] = 0.f; if (!(t.z > 0.f)) g[2] = 0.f; if (!(t.w > 0.f)) g[3] = 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float is = invstd[c + k], sc = is * (gamma ? gamma[c + k] : 1.f);
+      if (training) {
+        const float xh = (xv[k] - mean[c + k]) * is;
+        const float m0 = (float)red[c + k] * inv_count, m1 = (float)red[C + c + k] * inv_count;
+        o[k] = sc * (g[k] - m0 - xh * m1);
+      } else {
+        o[k] = sc * g[k];
+      }
+    }
+    if (dx.p) st4(dx.p + p * dx.ld + c, make_float4(o[0], o[1], o[2], o[3]));
+    if (dres.p) st4(dres.p + p * dres.ld + c, make_float4(g[0], g[1], g[2], g[3]));
+  }
+}
+
+static inline int shift_of(int v) { int s = 0; while ((1 << s) < v) ++s; return (1 << s) == v ? s : -1; }
+
+static void reduce_geometry(long long P, int C, dim3& grid, long long& slab) {
+  const int cq = C / 4;
+  const int cblocks = cdiv(cq, 32);
+  const int cq_w = cq < 32 ? cq : 32, ppw = 32 / cq_w;
+  long long want = (148LL * 8) / cblocks; if (want < 1) want = 1;
+  long long s = cdiv(P, 8LL * ppw * 16); if (s > want) s = want; if (s < 1) s = 1;
+  slab = (P + s - 1) / s;
+  grid = dim3((unsigned)cdiv(P, slab), cblocks);
+}
+
+bool fast_reduce_ok(const View& x) {
+  const int cq = x.c / 4;
+  return pix_contig(x) && x.c % 4 == 0 && (cq >= 32 || (32 % cq) == 0) && (long long)x.n * x.h * x.w >= 512;
+}
+
+int bn_stats_fast(const View& x, double* sums, cudaStream_t st) {
+  const long long P = (long long)x.n * x.h * x.w;
+  dim3 grid; long long slab;
+  reduce_geometry(P, x.c, grid, slab);
+  Rows none; none.p = nullptr; none.ld = 0;
+  colreduce_fast_kernel<0><<<grid, dim3(32, 8), 0, st>>>(rows_of(x), none, none, none, P, x.c, nullptr, nullptr, 0, sums,
+                                                        nullptr, slab);
+  return launched();
+}
+int bn_bwd_reduce_fast(const View& x, const View& y, const View& dy, const float* mean, const float* invstd, int act,
+                       double* red, cudaStream_t st) {
+  const long long P = (long long)x.n * x.h * x.w;
+  dim3 grid; long long slab;
+  reduce_geometry(P, x.c, grid, slab);
+  Rows none; none.p = nullptr; none.ld = 0;
+  colreduce_fast_kernel<1><<<grid, dim3(32, 8), 0, st>>>(rows_of(x), y.p ? rows_of(y) : none, rows_of(dy), none, P, x.c, mean,
+                                                        invstd, act, red, nullptr, slab);
+  return launched();
+}
+int act_bwd_bias_fast(const View& y, const View& dy, const View& dz, int act, float* dbias, cudaStream_t st) {
+  const long long P = (long long)dy.n * dy.h * dy.w;
+  dim3 grid; long long slab;
+  reduce_geometry(P, dy.c, grid, slab);
+  Rows none; none.p = nullptr; none.ld = 0;
+  colreduce_fast_kernel<2><<<grid, dim3(32, 8), 0, st>>>(none, y.p ? rows_of(y) : none, rows_of(dy), dz.p ? rows_of(dz) : none,
+                                                        P, dy.c, nullptr, nullptr, act, nullptr, dbias, slab);
+  return launched();
+}
+int bn_apply_fast(const View& x, const View& res, const View& y, const float* mean, const float* invstd, const float* gamma,
+                  const float* beta, int act, cudaStream_t st) {
+  const long long P = (long long)x.n * x.h * x.w;
+  const int cq = x.c / 4;
+  const long long total4 = P * cq;
+  long long blocks = cdiv(total4, 256 * 4); if (blocks > 148 * 16) blocks = 148 * 16; if (blocks < 1) blocks = 1;
+  Rows none; none.p = nullptr; none.ld = 0;
+  bn_apply_fast_kernel<<<(unsigned)blocks, 256, 0, st>>>(rows_of(x), res.p ? rows_of(res) : none, rows_of(y), total4, cq,
+                                                        shift_of(cq), mean, invstd, gamma, beta, act);
+  return launched();
+}
+int bn_bwd_apply_fast(const View& x, const View& y, const View& dy, const View& dx, const View& dres, const float* mean,
+                      const float* invstd, const float* gamma, int relu, int training, const double* red, long long count,
+                      cudaStream_t st) {
+  const long long P = (long long)x.n * x.h * x.w;
+  const int cq = x.c / 4;
+  const long long total4 = P * cq;
+  long long blocks = cdiv(total4, 256 * 4); if (blocks > 148 * 16) blocks = 148 * 16; if (blocks < 1) blocks = 1;
+  Rows none; none.p = nullptr; none.ld = 0;
+  bn_bwd_apply_fast_kernel<<<(unsigned)blocks, 256, 0, st>>>(rows_of(x), y.p ? rows_of(y) : none, rows_of(dy),
+                                                            dx.p ? rows_of(dx) : none, dres.p ? rows_of(dres) : none, total4, cq,
+                                                            shift_of(cq), x.c, mean, invstd, gamma, relu, training, red,
+                                                            (float)(1.0 / (double)count));
+  return launched();
+}
+
+}  // namespace segsde

@@ -120,4 +120,22 @@ __device__ __forceinline__ float u01(uint32_t x) {  // (0,1]
   return ((float)(x >> 8) + 1.0f) * (1.0f / 16777216.0f);
 }
 
+// single-output-channel fast paths (conv_small.cu); return SEGSDE_E_UNSUPPORTED when the shape is not theirs
+int c1_fwd(const View& x, const View& y, const float* w, const float* bias, const segsde_conv_desc_t* d, cudaStream_t st);
+int c1_dgrad(const View& dy, const float* w, const View& dx, const segsde_conv_desc_t* d, cudaStream_t st);
+int c1_wgrad(const View& x, const View& dy, float* dw, const segsde_conv_desc_t* d, cudaStream_t st);
+
+// bandwidth-tuned paths for pixel-contiguous tensors (bn_fast.cu)
+bool pix_contig(const View& v);
+bool fast_reduce_ok(const View& x);
+int bn_stats_fast(const View& x, double* sums, cudaStream_t st);
+int bn_bwd_reduce_fast(const View& x, const View& y, const View& dy, const float* mean, const float* invstd, int act,
+                       double* red, cudaStream_t st);
+int act_bwd_bias_fast(const View& y, const View& dy, const View& dz, int act, float* dbias, cudaStream_t st);
+int bn_apply_fast(const View& x, const View& res, const View& y, const float* mean, const float* invstd, const float* gamma,
+                  const float* beta, int act, cudaStream_t st);
+int bn_bwd_apply_fast(const View& x, const View& y, const View& dy, const View& dx, const View& dres, const float* mean,
+                      const float* invstd, const float* gamma, int relu, int training, const double* red, long long count,
+                      cudaStream_t st);
+
 }  // namespace segsde

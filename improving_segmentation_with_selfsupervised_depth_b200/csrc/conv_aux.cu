@@ -127,6 +127,8 @@ extern "C" int segsde_act_bwd_bias(const segsde_nhwc_t* y, const segsde_nhwc_t* 
   View vy = mk(y), vd = mk(dy), vz = mk(dz);
   if (act != SEGSDE_ACT_NONE && (!vy.p || !same_shape(vy, vd))) return SEGSDE_E_ARG;
   if (vz.p && !same_shape(vz, vd)) return SEGSDE_E_ARG;
+  if (fast_reduce_ok(vd) && (act == SEGSDE_ACT_NONE || pix_contig(vy)) && (!vz.p || pix_contig(vz)))
+    return act_bwd_bias_fast(vy, vd, vz, act, dbias, as_stream(stream));
   const long long P = (long long)vd.n * vd.h * vd.w;
   const int groups = cdiv(vd.c, 32);
   long long want = (148LL * 8) / groups; if (want < 1) want = 1;
@@ -134,5 +136,70 @@ extern "C" int segsde_act_bwd_bias(const segsde_nhwc_t* y, const segsde_nhwc_t* 
   const long long slab = (P + s - 1) / s;
   dim3 grid(groups, cdiv(P, slab)), block(32, 8);
   act_bwd_bias_kernel<<<grid, block, 0, as_stream(stream)>>>(vy, vd, vz, act, dbias, slab);
+  return launched();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Stem (7x7 / stride 2 on 3- or 6-channel NCHW images, resnet_encoder.py:92-93) as a tensor-core GEMM:
+// an im2col pass writes cols[n, oh, ow, (r*kw+s)*Cin + c] = (x[n,c,2oh-3+r,2ow-3+s] - 0.45)/0.225 (0 outside
+// the image, K padded with zeros to a multiple of 32), after which conv1 is a 1x1 convolution over a
+// Kpad-channel NHWC tensor and its wgrad is the 1x1 wgrad.
+// ---------------------------------------------------------------------------------------------------
+namespace segsde {
+// one CTA per 32 consecutive output pixels of a row: gather (k, pixel) with pixel-fastest reads (coalesced
+// along the image row), transpose through shared memory, write the 32 x Kpad block contiguously
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
+                                                          int C1, int C2, int N, int H, int W, int kh, int kw, int stride,
+                                                          int pad, int Ho, int Wo, int Kpad, float* __restrict__ cols) {
+  extern __shared__ float tile[];                 // [32][Kpad + 1]
+  const int segs = (Wo + 31) / 32;
+  int b = blockIdx.x;
+  const int seg = b % segs; b /= segs;
+  const int oh = b % Ho; const int n = b / Ho;
+  const int ow0 = seg * 32;
+  const int Ct = C1 + C2, K = kh * kw * Ct, ld = Kpad + 1;
+  for (int i = threadIdx.x; i < 32 * Kpad; i += blockDim.x) {
+    const int px = i & 31, k = i >> 5;
+    float v = 0.f;
+    const int ow = ow0 + px;
+    if (k < K && ow < Wo) {
+      const int c = k % Ct, tap = k / Ct, s = tap % kw, r = tap / kw;
+      const int h = oh * stride - pad + r, w = ow * stride - pad + s;
+      if (h >= 0 && h < H && w >= 0 && w < W) {
+        const float* src = c < C1 ? x1 + (((long long)n * C1 + c) * H + h) * W + w
+                                  : x2 + (((long long)n * C2 + (c - C1)) * H + h) * W + w;
+        v = (__ldg(src) - 0.45f) / 0.225f;
+      }
+    }
+    tile[px * ld + k] = v;
+  }
+  __syncthreads();
+  const int npx = min(32, Wo - ow0);
+  float* dst = cols + (((long long)n * Ho + oh) * Wo + ow0) * Kpad;
+  for (int i = threadIdx.x; i < npx * Kpad; i += blockDim.x) dst[i] = tile[(i / Kpad) * ld + (i % Kpad)];
+}
+// dst[r][0..cols_dst) = src[r][0..cols_src) zero-padded / truncated (row-major)
+__global__ void copy_rows_kernel(const float* __restrict__ src, int ld_src, float* __restrict__ dst, int ld_dst,
+                                 int rows, int ncopy) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * ld_dst) return;
+  const int r = i / ld_dst, c = i % ld_dst;
+  dst[i] = c < ncopy ? src[(long long)r * ld_src + c] : 0.f;
+}
+}  // namespace segsde
+
+extern "C" int segsde_stem_im2col(const float* x1, const float* x2, int c1, int c2, int n, int h, int w, int kh, int kw,
+                                  int stride, int pad, int kpad, float* cols, void* stream) {
+  if (!x1 || !cols || c1 < 1 || (c2 > 0 && !x2) || kpad < kh * kw * (c1 + c2)) return SEGSDE_E_ARG;
+  const int Ho = (h + 2 * pad - kh) / stride + 1, Wo = (w + 2 * pad - kw) / stride + 1;
+  const long long blocks = (long long)n * Ho * cdiv(Wo, 32);
+  const size_t smem = sizeof(float) * 32 * (kpad + 1);
+  stem_im2col_kernel<<<(unsigned)blocks, 256, smem, as_stream(stream)>>>(x1, x2, c1, c2, n, h, w, kh, kw, stride, pad, Ho, Wo,
+                                                                        kpad, cols);
+  return launched();
+}
+extern "C" int segsde_copy_rows(const float* src, int ld_src, float* dst, int ld_dst, int rows, int ncopy, void* stream) {
+  if (!src || !dst || rows < 1 || ld_dst < 1 || ncopy > ld_src || ncopy > ld_dst) return SEGSDE_E_ARG;
+  copy_rows_kernel<<<cdiv((long long)rows * ld_dst, 256), 256, 0, as_stream(stream)>>>(src, ld_src, dst, ld_dst, rows, ncopy);
   return launched();
 }

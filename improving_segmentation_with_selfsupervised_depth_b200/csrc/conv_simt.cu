@@ -334,6 +334,10 @@ extern "C" int segsde_conv2d_fwd(const segsde_nhwc_t* x1, const segsde_nhwc_t* x
   int rc = fill(p, x1, x2, y, d, false);
   if (rc) return rc;
   if (!w) return SEGSDE_E_ARG;
+  if (p.Cout == 1 && !p.x2.p) {
+    rc = c1_fwd(p.x1, p.y, w, bias, d, as_stream(stream));
+    if (rc != SEGSDE_E_UNSUPPORTED) return rc;
+  }
   p.w = w; p.bias = bias;
   dim3 grid(cdiv(p.P, BM), cdiv(p.Cout, BN));
   conv_fwd_kernel<<<grid, CT, 0, as_stream(stream)>>>(p);
@@ -349,6 +353,10 @@ extern "C" int segsde_conv2d_dgrad(const segsde_nhwc_t* dy, const float* w, cons
   int rc = fill(p, dx1, dx2, dy, d, true);
   if (rc) return rc;
   if (!w || p.nchw) return SEGSDE_E_ARG;
+  if (p.Cout == 1 && p.x1.p && !dx2) {
+    rc = c1_dgrad(p.y, w, p.x1, d, as_stream(stream));
+    if (rc != SEGSDE_E_UNSUPPORTED) return rc;
+  }
   p.w = w; p.bias = nullptr;
   const bool refl = p.pad_mode == SEGSDE_PAD_REFLECT;
   const int off = refl ? p.pad : 0;
@@ -367,6 +375,10 @@ extern "C" int segsde_conv2d_wgrad(const segsde_nhwc_t* x1, const segsde_nhwc_t*
   int rc = fill(p, x1, x2, dy, d, false);
   if (rc) return rc;
   if (!dw) return SEGSDE_E_ARG;
+  if (p.Cout == 1 && !p.x2.p && !dbias) {
+    rc = c1_wgrad(p.x1, p.y, dw, d, as_stream(stream));
+    if (rc != SEGSDE_E_UNSUPPORTED) return rc;
+  }
   p.w = nullptr; p.bias = nullptr;
   const int gx = cdiv(p.Cout, BM), gy = cdiv(p.Ktot, BN);
   long long want = (148LL * 6) / ((long long)gx * gy);

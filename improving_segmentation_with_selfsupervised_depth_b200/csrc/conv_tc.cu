@@ -458,7 +458,7 @@ extern "C" int segsde_conv2d_fwd_tc(const segsde_nhwc_t* x1, const segsde_nhwc_t
   if (!x1 || !x1->ptr || !w || !y || !y->ptr || !d) return SEGSDE_E_ARG;
   if (!tc_init()) return SEGSDE_E_UNSUPPORTED;
   if (d->pad_mode != SEGSDE_PAD_ZERO || d->up1 || d->nchw_norm_in) return SEGSDE_E_UNSUPPORTED;
-  if (d->stride != 1) return SEGSDE_E_UNSUPPORTED;   // stride 2 (TMA element strides) not enabled yet
+  if (d->stride != 1 && d->stride != 2) return SEGSDE_E_UNSUPPORTED;   // stride 2 = TMA element strides
   View v1 = mk(x1), v2 = mk(x2), vy = mk(y);
   const int C1 = v1.c, C2 = v2.p ? v2.c : 0, Cout = vy.c;
   if (C1 % 32 || C2 % 32 || Cout % 64) return SEGSDE_E_UNSUPPORTED;

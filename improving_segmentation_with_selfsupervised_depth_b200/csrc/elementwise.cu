@@ -83,9 +83,11 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int C, doubl
                                    float* __restrict__ rmean, float* __restrict__ rvar) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const double m = sums[c] / count;
-  double var = sums[C + c] / count - m * m;
+  // sums hold sum(x - s), sum((x - s)^2) and the shift s (0 on the generic path)
+  const double ms = sums[c] / count;
+  double var = sums[C + c] / count - ms * ms;
   if (var < 0.0) var = 0.0;
+  const double m = ms + sums[2 * C + c];
   mean[c] = (float)m;
   invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
   if (rmean) {
@@ -400,6 +402,7 @@ static long long slab_for(const View& x, int& nslabs) {
 extern "C" int segsde_bn_stats(const segsde_nhwc_t* x, double* sums, void* stream) {
   if (!x || !x->ptr || !sums) return SEGSDE_E_ARG;
   View v = mk(x), none = mk(nullptr);
+  if (fast_reduce_ok(v)) return bn_stats_fast(v, sums, as_stream(stream));
   int ns; const long long slab = slab_for(v, ns);
   dim3 grid(cdiv(v.c, 32), ns), block(32, 8);
   chan_reduce_kernel<0><<<grid, block, 0, as_stream(stream)>>>(v, none, none, nullptr, nullptr, 0, sums, slab);
@@ -428,6 +431,8 @@ extern "C" int segsde_bn_apply(const segsde_nhwc_t* x, const float* mean, const 
   if (!same_shape(vx, vy) || (vr.p && !same_shape(vx, vr))) return SEGSDE_E_ARG;
   if (act != SEGSDE_ACT_NONE && act != SEGSDE_ACT_RELU) return SEGSDE_E_UNSUPPORTED;
   const bool v4 = vec4_ok(vx) && vec4_ok(vy) && (!vr.p || vec4_ok(vr));
+  if (pix_contig(vx) && pix_contig(vy) && (!vr.p || pix_contig(vr)))
+    return bn_apply_fast(vx, vr, vy, mean, invstd, gamma, beta, act, as_stream(stream));
   DISPATCH_VEC(v4, bn_apply_kernel, vx, vx, mean, invstd, gamma, beta, vr, vy, act);
   return launched();
 }
@@ -438,6 +443,8 @@ extern "C" int segsde_bn_bwd_reduce(const segsde_nhwc_t* x, const segsde_nhwc_t*
   if (relu && (!y || !y->ptr)) return SEGSDE_E_ARG;
   View vx = mk(x), vy = mk(y), vd = mk(dy);
   if (!same_shape(vx, vd)) return SEGSDE_E_ARG;
+  if (fast_reduce_ok(vx) && pix_contig(vd) && (!relu || pix_contig(vy)))
+    return bn_bwd_reduce_fast(vx, vy, vd, mean, invstd, act, red, as_stream(stream));
   int ns; const long long slab = slab_for(vx, ns);
   dim3 grid(cdiv(vx.c, 32), ns), block(32, 8);
   chan_reduce_kernel<1><<<grid, block, 0, as_stream(stream)>>>(vx, vy, vd, mean, invstd, relu, red, slab);
@@ -452,7 +459,12 @@ extern "C" int segsde_bn_bwd_apply(const segsde_nhwc_t* x, const segsde_nhwc_t* 
   View vx = mk(x), vy = mk(y), vd = mk(dy), vdx = mk(dx), vdr = mk(dres);
   if (relu && !vy.p) return SEGSDE_E_ARG;
   int rc = SEGSDE_OK;
-  if (vdx.p || vdr.p) {
+  const bool fast = pix_contig(vx) && pix_contig(vd) && (!relu || pix_contig(vy)) && (!vdx.p || pix_contig(vdx)) &&
+                    (!vdr.p || pix_contig(vdr));
+  if ((vdx.p || vdr.p) && fast) {
+    rc = bn_bwd_apply_fast(vx, vy, vd, vdx, vdr, mean, invstd, gamma, relu, training, red, count, as_stream(stream));
+    if (rc) return rc;
+  } else if (vdx.p || vdr.p) {
     const bool v4 = vec4_ok(vx) && vec4_ok(vd) && (!relu || vec4_ok(vy)) && (!vdx.p || vec4_ok(vdx)) &&
                     (!vdr.p || vec4_ok(vdr));
     DISPATCH_VEC(v4, bn_bwd_apply_kernel, vx, vx, vy, vd, mean, invstd, gamma, relu, training, red,

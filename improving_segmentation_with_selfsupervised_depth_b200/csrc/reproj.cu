@@ -32,6 +32,7 @@ struct ReprojK {
   float* loss_partial; float* ident_sel; float* gdisp; float* gT_partial;
   float inv_count;
   int tiles_x, tiles_y;
+  float* ident_cache; int ident_mode;
 };
 
 struct UpW {  // bilinear source taps of the low-res disparity for one full-res pixel
@@ -80,12 +81,10 @@ __device__ __forceinline__ void warp_pixel(const float* __restrict__ src, int H,
   const float Z = P[8] * cx + P[9] * cy + P[10] * cz + P[11];
   const float z = Z + 1e-7f;
   float px = X / z, py = Y / z;
-  // Project3D normalisation followed by grid_sample's un-normalisation (kept op-for-op so the
-  // sub-pixel rounding matches the reference)
-  float gx = (px / (float)(W - 1) - 0.5f) * 2.f;
-  float gy = (py / (float)(H - 1) - 0.5f) * 2.f;
-  float ix = ((gx + 1.f) / 2.f) * (float)(W - 1);
-  float iy = ((gy + 1.f) / 2.f) * (float)(H - 1);
+  // Project3D's normalisation ((p/(W-1) - 0.5)*2) and grid_sample's un-normalisation (((g+1)/2)*(W-1)) are
+  // exact inverses; composing them only adds a few ulp of rounding and four divisions per sample, so the
+  // pixel coordinate is used directly.
+  float ix = px, iy = py;
   float mx = 1.f, my = 1.f;
   const float maxx = (float)(W - 1), maxy = (float)(H - 1);
   if (!(ix > 0.f)) { ix = 0.f; mx = 0.f; } else if (ix >= maxx) { ix = maxx; mx = 0.f; }
@@ -117,10 +116,11 @@ struct Stats { float mu_x, mu_y, sxx, syy, sxy; };
 // SSIM of monodepth_layers.py:240-254 for one channel at one centre; also returns the statistics.
 __device__ __forceinline__ float ssim_from_sums(float sx, float sy, float sxx, float syy, float sxy,
                                                 Stats* st) {
-  const float mu_x = sx / 9.f, mu_y = sy / 9.f;
-  const float sig_x = sxx / 9.f - mu_x * mu_x;
-  const float sig_y = syy / 9.f - mu_y * mu_y;
-  const float sig_xy = sxy / 9.f - mu_x * mu_y;
+  constexpr float i9 = 1.f / 9.f;      // AvgPool2d(3,1): multiply instead of five fp32 divisions per window
+  const float mu_x = sx * i9, mu_y = sy * i9;
+  const float sig_x = sxx * i9 - mu_x * mu_x;
+  const float sig_y = syy * i9 - mu_y * mu_y;
+  const float sig_xy = sxy * i9 - mu_x * mu_y;
   const float n = (2.f * mu_x * mu_y + 1e-4f) * (2.f * sig_xy + 9e-4f);
   const float d = (mu_x * mu_x + mu_y * mu_y + 1e-4f) * (sig_x + sig_y + 9e-4f);
   if (st) { st->mu_x = mu_x; st->mu_y = mu_y; st->sxx = sig_x; st->syy = sig_y; st->sxy = sig_xy; }
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(NTHREADS) reproj_kernel(ReprojK k) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       s_tgt[c * NP + i] = in ? __ldg(k.tgt + ((size_t)b * 3 + c) * plane + o) : 0.f;
-      if (automask)
+      if (automask && k.ident_mode != 2)
         for (int f = 0; f < F; ++f)
           s_src[(f * 3 + c) * NP + i] = in ? __ldg(k.src[f] + ((size_t)b * 3 + c) * plane + o) : 0.f;
     }
@@ -265,30 +265,44 @@ __global__ void __launch_bounds__(NTHREADS) reproj_kernel(ReprojK k) {
         wo[(dy + 1) * 3 + dx + 1] = (reflect_idx(cy + dy, H) - ry0) * RW + (reflect_idx(cx + dx, W) - rx0);
     const int ctr = wo[4];
     float cand[4] = {0.f, 0.f, 0.f, 0.f};   // [identity f0, identity f1, reproj f0, reproj f1]
-    const int nimg = automask ? 2 * F : F;
+    // images: m = 0,1 reprojected frames; m = 2,3 raw source frames (identity candidates).  The identity
+    // candidates do not depend on the scale: scale 0 stores them (ident_mode 1), coarser scales read them back
+    // (ident_mode 2) instead of recomputing two SSIM windows per pixel.
+    const bool id_compute = automask && k.ident_mode != 2;
     float ssim_acc[4] = {0.f, 0.f, 0.f, 0.f}, l1_acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       float yw[9], sy = 0.f, syy = 0.f;
 #pragma unroll
-      for (int t = 0; t < 9; ++t) { yw[t] = s_tgt[c * NP + wo[t]]; sy += yw[t]; syy += yw[t] * yw[t]; }
-      for (int m = 0; m < nimg; ++m) {
-        // m < F : reprojected frame m ; m >= F : raw source frame m-F (identity)
-        const float* X = (m < F) ? (s_pred + (m * 3 + c) * NP) : (s_src + ((m - F) * 3 + c) * NP);
+      for (int t = 0; t < 9; ++t) { yw[t] = s_tgt[c * NP + wo[t]]; sy += yw[t]; syy = fmaf(yw[t], yw[t], syy); }
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int f = m & 1;
+        if (f >= F || (m >= 2 && !id_compute)) continue;
+        const float* X = (m < 2) ? (s_pred + (f * 3 + c) * NP) : (s_src + (f * 3 + c) * NP);
         l1_acc[m] += fabsf(yw[4] - X[ctr]);
         if (!no_ssim) {
           float sx = 0.f, sxx = 0.f, sxy = 0.f;
 #pragma unroll
-          for (int t = 0; t < 9; ++t) { const float xv = X[wo[t]]; sx += xv; sxx += xv * xv; sxy += xv * yw[t]; }
+          for (int t = 0; t < 9; ++t) { const float xv = X[wo[t]]; sx += xv; sxx = fmaf(xv, xv, sxx); sxy = fmaf(xv, yw[t], sxy); }
           const float v = ssim_from_sums(sx, sy, sxx, syy, sxy, nullptr);
           ssim_acc[m] += fminf(fmaxf(v, 0.f), 1.f);
         }
       }
     }
-    for (int m = 0; m < nimg; ++m) {
-      const float l1 = l1_acc[m] / 3.f;
-      const float v = no_ssim ? l1 : 0.85f * (ssim_acc[m] / 3.f) + 0.15f * l1;
-      if (m < F) cand[2 + m] = v; else cand[m - F] = v;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int f = m & 1;
+      if (f >= F) continue;
+      const float l1 = l1_acc[m] * (1.f / 3.f);
+      const float v = no_ssim ? l1 : 0.85f * (ssim_acc[m] * (1.f / 3.f)) + 0.15f * l1;
+      if (m < 2) cand[2 + f] = v;
+      else if (id_compute) {
+        cand[f] = v;
+        if (k.ident_mode == 1 && is_own) k.ident_cache[(((size_t)b * F + f) * H + cy) * W + cx] = v;
+      } else if (automask) {
+        cand[f] = __ldg(k.ident_cache + (((size_t)b * F + f) * H + cy) * W + cx);
+      }
     }
     // candidates in the reference's order: identity (+noise) first, then reprojection
     float best = 3.4e38f; int best_i = -1; int n_id = 0;
@@ -601,6 +615,8 @@ extern "C" int segsde_reproj_fused(const segsde_reproj_args_t* a, void* stream) 
   k.gT_partial = a->gT_partial;
   k.inv_count = (float)(1.0 / ((double)a->B * a->H * a->W));
   k.tiles_x = cdiv(a->W, TX); k.tiles_y = cdiv(a->H, TY);
+  k.ident_cache = a->ident_cache; k.ident_mode = a->ident_cache ? a->ident_mode : 0;
+  if (k.ident_mode < 0 || k.ident_mode > 2) return SEGSDE_E_ARG;
   dim3 grid(k.tiles_x, k.tiles_y, a->B), block(NTHREADS);
   if (a->gdisp) {
     const size_t sm = reproj_smem_bytes<true>();

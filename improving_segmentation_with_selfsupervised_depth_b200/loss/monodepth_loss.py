@@ -40,6 +40,10 @@ class _MonoLossFn(torch.autograd.Function):
         Kc, iKc = K.contiguous(), inv_K.contiguous()
         Tc = [t.detach().contiguous() for t in Ts]
         owner._step += 1
+        # identity candidates are scale independent: computed by the scale-0 launch, re-read by the others
+        ident = None
+        if not owner.disable_automasking and not owner.avg_reprojection and S > 1:
+            ident = torch.empty(B, F, H, W, device=dev, dtype=torch.float32)
         for s in range(S):
             d = disps[s].detach()
             if not d.is_contiguous():
@@ -57,6 +61,8 @@ class _MonoLossFn(torch.autograd.Function):
             a.min_depth, a.max_depth, a.flags = owner.min_depth, owner.max_depth, flags
             a.loss_partial = partial.data_ptr()
             a.ident_sel = sel_out[s].data_ptr() if sel_out is not None else None
+            if ident is not None:
+                a.ident_cache, a.ident_mode = ident.data_ptr(), (1 if s == 0 else 2)
             if need_grad:
                 g = torch.zeros_like(d)
                 gdisps.append(g)

@@ -210,7 +210,7 @@ class _BatchNormFn(torch.autograd.Function):
         mean = torch.empty(c, device=dev, dtype=torch.float32)
         invstd = torch.empty(c, device=dev, dtype=torch.float32)
         if training:
-            sums = torch.zeros(2 * c, device=dev, dtype=torch.float64)
+            sums = torch.zeros(3 * c, device=dev, dtype=torch.float64)
             A.call("segsde_bn_stats", C.byref(view(x)), A.ptr(sums), st)
             A.call("segsde_bn_finalize", A.ptr(sums), C.c_int(c), C.c_int64(n * h * w), C.c_float(eps),
                    C.c_float(momentum), A.ptr(mean), A.ptr(invstd), A.ptr(running_mean), A.ptr(running_var), st)

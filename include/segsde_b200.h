@@ -102,6 +102,12 @@ int segsde_weight_transpose_flip(const float* w, float* wt, int cout, int kh, in
                                  int c_count, void* stream);
 int segsde_act_bwd_bias(const segsde_nhwc_t* y, const segsde_nhwc_t* dy, const segsde_nhwc_t* dz, int act,
                         float* dbias, void* stream);
+/* Stem as a GEMM: cols[n,oh,ow,(r*kw+s)*C + c] = (x[n,c,oh*stride-pad+r,ow*stride-pad+s]-0.45)/0.225, zero outside
+ * the image and for k >= kh*kw*C (kpad: K rounded up to a multiple of 32).  x1/x2: NCHW planar frames.
+ * copy_rows: dst[r][c] = c < ncopy ? src[r][c] : 0 (weight matrix <-> its K-padded form). */
+int segsde_stem_im2col(const float* x1, const float* x2, int c1, int c2, int n, int h, int w, int kh, int kw,
+                       int stride, int pad, int kpad, float* cols, void* stream);
+int segsde_copy_rows(const float* src, int ld_src, float* dst, int ld_dst, int rows, int ncopy, void* stream);
 /* 1 if this process can run the tensor-core path (driver entry point for tensor maps found). */
 int segsde_tc_available(void);
 
@@ -116,7 +122,8 @@ int segsde_act_bwd(const segsde_nhwc_t* y, const segsde_nhwc_t* dy, const segsde
  * joint_segmentation_depth_decoder.py:43).  Train mode = batch statistics (biased var for
  * normalisation, unbiased for the running update, momentum as torch).
  * ------------------------------------------------------------------------------------------- */
-/* sums[0..C) = sum x, sums[C..2C) = sum x^2 (fp64, must be zero-filled). */
+/* sums: 3C doubles, zero-filled: [0,C) = sum (x-s), [C,2C) = sum (x-s)^2, [2C,3C) = per-channel shift s
+ * (0 on the generic path, x at pixel 0 on the fast path) — consumed by segsde_bn_finalize. */
 int segsde_bn_stats(const segsde_nhwc_t* x, double* sums, void* stream);
 /* mean/invstd from sums; running stats update when running_mean != NULL. count = N*H*W. */
 int segsde_bn_finalize(const double* sums, int c, int64_t count, float eps, float momentum,
@@ -215,6 +222,11 @@ typedef struct {
   float* ident_sel;       /* [B,H,W] 1.0 where a reprojection candidate won, or NULL */
   float* gdisp;           /* [B,1,hs,ws] d(mean min-loss)/d disp, accumulated (zero-filled), or NULL */
   float* gT_partial;      /* [F][B][tiles][12] per-block d/dP partials (only with gdisp) */
+  /* The identity (auto-mask) candidates do not depend on the scale: with ident_mode 1 the launch stores them
+   * into ident_cache [B,F,H,W]; with ident_mode 2 it reads them back instead of recomputing the two SSIM
+   * windows per pixel.  NULL / 0 = always compute. */
+  float* ident_cache;
+  int32_t ident_mode;
 } segsde_reproj_args_t;
 
 int segsde_reproj_num_partials(int B, int H, int W);  /* = B * tiles */

@@ -94,3 +94,29 @@ def test_tc_conv_fwd_bwd(case):
     if bias:
         close(gb.grad, b.grad, "dbias")
     assert A.launch_count() > n0
+
+
+@pytest.mark.parametrize("k,cin,cout,H,W", [(3, 64, 128, 32, 64), (1, 64, 128, 32, 64), (3, 128, 256, 18, 36), (1, 256, 512, 16, 32)])
+def test_tc_conv_stride2(k, cin, cout, H, W):
+    """ResNet stride-2 convolutions: 3x3 through TMA element strides (fprop) + zero-stuffed dy (dgrad/wgrad),
+    1x1 through the ::2 strided view."""
+    A, ops = _mods()
+    ops.USE_TC = True
+    g = torch.Generator().manual_seed(k * 100 + cin)
+    x = torch.randn(2, cin, H, W, generator=g).requires_grad_()
+    w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).requires_grad_()
+    y = F.conv2d(x, w, None, 2, k // 2)
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy)
+    gx = x.detach().cuda().requires_grad_()
+    gw = w.detach().cuda().contiguous(memory_format=torch.channels_last).requires_grad_()
+    ops.PROFILE = []
+    ops.PROFILE_DESC = []
+    gy = ops.conv2d(gx, gw, None, stride=2, pad=k // 2)
+    gy.backward(dy.cuda())
+    torch.cuda.synchronize()
+    ops.PROFILE, ops.PROFILE_DESC = None, None
+    assert gy.shape == y.shape
+    assert rel_err(gy, y) < TOL, "fprop"
+    assert rel_err(gx.grad, x.grad) < TOL, "dgrad"
+    assert rel_err(gw.grad, w.grad) < TOL, "wgrad"
