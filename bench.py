@@ -92,6 +92,12 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # CPU arm: the reference algorithm (oracle port; /root/reference cannot travel to the GPU box)
 # --------------------------------------------------------------------------------------------------
+def cpu_threads():
+    """Intra-op threads of the CPU arm: all host cores up to 32 (beyond that torch's CPU conv/BN kernels on this
+    batch-2 workload get slower, not faster — 128 threads measured 10x slower than 8)."""
+    return int(os.environ.get("SEGSDE_CPU_THREADS", min(os.cpu_count() or 1, 32)))
+
+
 def cpu_step_factory(B, H, W):
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -127,7 +133,7 @@ def run_reference(args):
     if rank != 0:
         return
     import torch
-    cores = os.cpu_count()
+    cores = cpu_threads()
     torch.set_num_threads(cores)
     B, H, W = args.ref_batch, args.height, args.width
     step = cpu_step_factory(B, H, W)
@@ -267,7 +273,7 @@ def run_b200(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         import torch as _t
-        cores = os.cpu_count()
+        cores = cpu_threads()
         _t.set_num_threads(cores)
         cstep = cpu_step_factory(args.ref_batch, H, W)
         t0 = time.perf_counter()

@@ -192,7 +192,7 @@ def test_model_tensor_core_path_vs_oracle(contracts):
         assert "fprop" in {k for k, *_ in ops.PROFILE}
         feats = model.models["encoder"].features
         for i in range(5):
-            assert l2(feats[i], ref["features"][i]) < 1e-2, ("feature", i)
+            assert l2(feats[i], ref["features"][i]) < 2e-2, ("feature", i)
             assert l2(out[("upconv", i)], ref[("upconv", i)]) < 3e-2, ("upconv", i)
         for s in range(4):
             assert (out[("disp", s)].cpu() - ref[("disp", s)]).abs().max().item() < 5e-3, s
