@@ -434,3 +434,83 @@ def synthetic_state_dict(template, seed=0):
         else:                            # biases
             out[k] = torch.randn(shape, generator=g) * 0.05
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# segmentation decoders (joint seg + depth configurations)
+# ------------------------------------------------------------------------------------------------
+
+
+def _self_attention(sd, p, x):
+    """SelfAttention.forward, models/model_parts.py:43-45."""
+    return _conv(sd, p + ".conv", x, 1, 1) * torch.sigmoid(_conv(sd, p + ".attention", x, 1, 1))
+
+
+def joint_seg_depth_decoder(sd, prefix, feats, layers=(9,), output_stride=1, head_inter=True, mode=None,
+                            dropout_masks=None, depth_args=None):
+    """JointSegDepthDecoder.forward, models/joint_segmentation_depth_decoder.py:55-75 (layer_dropout = 0).
+    dropout_masks: {"aspp": mask, "head": mask} replayed 0/1 masks (nn.Dropout(0.5) / nn.Dropout(head_dropout=0.1))."""
+    mode = mode or BNMode()
+    dm = dropout_masks or {}
+    da = depth_args or {}
+    dec = depth_decoder(sd, prefix + "unet_dec.", feats, mode=mode, dropout_mask=dm.get("aspp"),
+                        intermediate_aspp=da.get("intermediate_aspp", True), aspp_rates=da.get("aspp_rates", (6, 12, 18)),
+                        aspp_pooling=da.get("aspp_pooling", True))
+    last_layer = 9
+    seg_size = tuple((feats[last_layer] if last_layer <= 4 else dec[("upconv", 9 - last_layer)]).shape[2:])
+    out_size = tuple(int(v) // output_stride for v in seg_size)
+    stacked = []
+    for layer in layers:
+        src = feats[layer] if layer <= 4 else dec[("upconv", 9 - layer)]
+        proj = _conv(sd, "%sproject.seg%d.0" % (prefix, layer), src)
+        stacked.append(F.interpolate(proj, size=out_size, mode="bilinear", align_corners=False))
+    x = torch.cat(stacked, 1)
+    if head_inter:      # head = [Identity, conv3x3, BN, ReLU, Dropout, conv1x1] -> indices 1,2,5
+        x = F.relu(_bn(sd, prefix + "head.2", _conv(sd, prefix + "head.1", x, 1, 1), mode))
+        if mode.training:
+            x = x * dm["head"] / 0.9
+        x = _conv(sd, prefix + "head.5", x)
+    else:               # head = [Identity, Identity, conv1x1]
+        x = _conv(sd, prefix + "head.2", x)
+    if out_size != seg_size:
+        x = F.interpolate(x, size=seg_size, mode="bilinear", align_corners=False)
+    return x
+
+
+def pad_decoder(sd, prefix, feats, distillation_layer=7, final_layer=9, side_output=True, output_stride=1, mode=None,
+                dropout_masks=None, depth_args=None):
+    """PAD.forward, models/joint_segmentation_depth_decoder.py:134-184.
+    dropout_masks: {"depth": aspp mask of depth_dec, "seg": aspp mask of seg_dec}."""
+    mode = mode or BNMode()
+    dm = dropout_masks or {}
+    da = depth_args or {}
+    kw = dict(mode=mode, intermediate_aspp=da.get("intermediate_aspp", True), aspp_rates=da.get("aspp_rates", (6, 12, 18)),
+              aspp_pooling=da.get("aspp_pooling", True))
+    n_up = da.get("n_upconv", 4)
+    di = 9 - distillation_layer
+    first, second = list(range(n_up, di - 1, -1)), list(range(di - 1, -1, -1))
+    depth = depth_decoder(sd, prefix + "depth_dec.", feats, exec_layer=first, dropout_mask=dm.get("depth"), **kw)
+    seg = depth_decoder(sd, prefix + "seg_dec.", feats, exec_layer=first, dropout_mask=dm.get("seg"),
+                        enable_disparity=False, scales=(), **kw)
+    mid = ("upconv", di)
+    out = {}
+    if side_output:
+        inter = _conv(sd, prefix + "seg_intermediate_head.0", seg[mid])
+    sa_depth = _self_attention(sd, prefix + "sa_depth", depth[mid])
+    sa_seg = _self_attention(sd, prefix + "sa_seg", seg[mid])
+    merged_seg, merged_depth = seg[mid] + sa_depth, depth[mid] + sa_seg
+    depth.update(depth_decoder(sd, prefix + "depth_dec.", feats, x=merged_depth, exec_layer=second, **kw))
+    seg2 = depth_decoder(sd, prefix + "seg_dec.", feats, x=merged_seg, exec_layer=second, enable_disparity=False,
+                         scales=(), **kw)
+    final = _conv(sd, prefix + "seg_final_head.0", seg2[("upconv", 9 - final_layer)])
+    seg_size = tuple(feats[0].shape[2:])
+    out_size = tuple(int(v) // output_stride for v in seg_size)
+    if out_size != seg_size:
+        final = F.interpolate(final, size=seg_size, mode="bilinear", align_corners=False)
+        if side_output:
+            inter = F.interpolate(inter, size=seg_size, mode="bilinear", align_corners=False)
+    out.update(depth)
+    out["semantics"] = final
+    if side_output:
+        out["intermediate_semantics"] = inter
+    return out

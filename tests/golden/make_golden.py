@@ -140,6 +140,55 @@ def main():
         out[p + "grad_pose3"] = dict(model.named_parameters())["models.pose.net.3.weight"].grad.numpy()
         out[p + "bn1_running_mean"] = model.state_dict()["models.encoder.encoder.bn1.running_mean"].numpy()
         out[p + "bn1_running_var"] = model.state_dict()["models.encoder.encoder.bn1.running_var"].numpy()
+    # ---- 5. segmentation decoders (JointSegDepthDecoder, PAD): fwd + CE loss + grads -----------------
+    from loss.loss import cross_entropy2d as ref_ce2
+    H, W = 64, 96
+    for name in ("segdec_r50", "pad_r50"):
+        cfg = dict(cfgs[name])
+        with quiet():
+            model = ref_models.get_model(cfg, 19)
+        sd = O.synthetic_state_dict(model.state_dict(), seed=2)
+        model.load_state_dict(sd)
+        model.train()
+        inputs = O.synthetic_inputs(B, H, W, seed=6, labels=True)
+        rec = {}
+
+        def grab(key):
+            def hook(m, i, o):
+                rec[key] = (i[0].detach().clone(), o.detach().clone())
+            return hook
+        hooks = []
+        if name == "segdec_r50":
+            dec = model.models["segmentation"]
+            hooks.append(dec.unet_dec.convs[("upconv", 4, 0)].project[3].register_forward_hook(grab("aspp")))
+            hooks.append(dec.head[4].register_forward_hook(grab("head")))
+        else:
+            dec = model.models["mtl_decoder"]
+            hooks.append(dec.depth_dec.convs[("upconv", 4, 0)].project[3].register_forward_hook(grab("depth")))
+            hooks.append(dec.seg_dec.convs[("upconv", 4, 0)].project[3].register_forward_hook(grab("seg")))
+        torch.manual_seed(41)
+        with quiet():
+            rout = model(inputs)
+        for h in hooks:
+            h.remove()
+        p = "seg_%s_" % name
+        for key, (i_, o_) in rec.items():
+            mask = torch.where(i_ != 0, (o_ != 0), torch.ones_like(o_, dtype=torch.bool))
+            out[p + "mask_" + key] = np.packbits(mask.numpy().reshape(-1))
+            out[p + "mask_" + key + "_shape"] = np.array(mask.shape)
+        loss = ref_ce2(input=rout["semantics"], target=inputs["lbl"])
+        if "intermediate_semantics" in rout:
+            loss = (loss + ref_ce2(input=rout["intermediate_semantics"], target=inputs["lbl"])) / 2
+            out[p + "intermediate"] = rout["intermediate_semantics"].detach().numpy()
+        loss.backward()
+        out[p + "semantics"] = rout["semantics"].detach().numpy()[:, :, ::4, ::4].copy()
+        out[p + "loss"] = loss.item()
+        names = [n for n, q in model.named_parameters() if q.grad is not None]
+        out[p + "grad_names"] = np.array(names)
+        out[p + "grad_norms"] = np.array([dict(model.named_parameters())[n].grad.norm().item() for n in names])
+        if name == "pad_r50":
+            for s_ in range(4):
+                out[p + "disp%d" % s_] = rout[("disp", s_)].detach().numpy()
     np.savez_compressed(os.path.join(HERE, "reference_golden.npz"), **out)
     print("wrote", os.path.join(HERE, "reference_golden.npz"),
           os.path.getsize(os.path.join(HERE, "reference_golden.npz")) // 1024, "KiB")

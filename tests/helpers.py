@@ -50,3 +50,9 @@ def unpack_mask(golden, prefix):
     shape = tuple(int(v) for v in golden[prefix + "dropout_shape"])
     bits = np.unpackbits(golden[prefix + "dropout_mask"])[:int(np.prod(shape))]
     return torch.from_numpy(bits.reshape(shape).astype(np.float32))
+
+
+def unpack_named_mask(golden, key):
+    shape = tuple(int(v) for v in golden[key + "_shape"])
+    bits = np.unpackbits(golden[key])[:int(np.prod(shape))]
+    return torch.from_numpy(bits.reshape(shape).astype(np.float32))

@@ -211,3 +211,53 @@ def test_model_tensor_core_path_vs_oracle(contracts):
     finally:
         ops.PROFILE = None
         ops.USE_TC = False
+
+
+@pytest.mark.parametrize("name", ["segdec_r50", "pad_r50"])
+def test_seg_decoders_vs_reference_golden(golden, contracts, name):
+    """JointSegDepthDecoder / PAD (+ SelfAttention gate, bilinear resize, seg heads) and cross_entropy2d through the
+    drop-in API against the reference outputs: logits 2e-4, loss 2e-5, per-parameter gradient norms 3e-2."""
+    import improving_segmentation_with_selfsupervised_depth_b200 as P
+    from improving_segmentation_with_selfsupervised_depth_b200 import ops
+    from improving_segmentation_with_selfsupervised_depth_b200.loss.loss import cross_entropy2d
+    from helpers import unpack_named_mask
+    ops.USE_TC = False
+    models, _ = P.install_dropin()
+    H, W, B = 64, 96, 2
+    c = contracts[name]
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = models.get_model(dict(c["cfg"]), 19)
+    sd = O.synthetic_state_dict({k: torch.empty(s) for k, s in c["state_dict"].items()}, seed=2)
+    model.load_state_dict(sd)
+    model = model.cuda().train()
+    p = "seg_%s_" % name
+    if name == "segdec_r50":
+        dec = model.models["segmentation"]
+        dec.unet_dec.convs[("upconv", 4, 0)].project[3].replay_mask = unpack_named_mask(golden, p + "mask_aspp")
+        dec.head[4].replay_mask = unpack_named_mask(golden, p + "mask_head")
+    else:
+        dec = model.models["mtl_decoder"]
+        dec.depth_dec.convs[("upconv", 4, 0)].project[3].replay_mask = unpack_named_mask(golden, p + "mask_depth")
+        dec.seg_dec.convs[("upconv", 4, 0)].project[3].replay_mask = unpack_named_mask(golden, p + "mask_seg")
+    inputs = {k: v.cuda() for k, v in O.synthetic_inputs(B, H, W, seed=6, labels=True).items()}
+    with contextlib.redirect_stdout(io.StringIO()):
+        out = model(inputs)
+    assert rel_err(out["semantics"][:, :, ::4, ::4], golden[p + "semantics"]) < 2e-4
+    loss = cross_entropy2d(input=out["semantics"], target=inputs["lbl"])
+    if "intermediate_semantics" in out:
+        assert rel_err(out["intermediate_semantics"], golden[p + "intermediate"]) < 2e-4
+        for s in range(4):
+            assert rel_err(out[("disp", s)], golden[p + "disp%d" % s]) < 2e-4
+        loss = ops.add(loss.reshape(1, 1, 1, 1), cross_entropy2d(input=out["intermediate_semantics"],
+                                                                 target=inputs["lbl"]).reshape(1, 1, 1, 1)).reshape(()) / 2
+    assert abs(loss.item() - float(golden[p + "loss"])) < 2e-5 * abs(float(golden[p + "loss"]))
+    loss.backward()
+    params = dict(model.named_parameters())
+    names = [str(n) for n in golden[p + "grad_names"]]
+    bad = []
+    for n, ref in zip(names, golden[p + "grad_norms"]):
+        g = params[n].grad
+        v = 0.0 if g is None else g.norm().item()
+        if abs(v - ref) > 3e-2 * ref + 1e-7:
+            bad.append((n, v, float(ref)))
+    assert not bad, bad[:6]

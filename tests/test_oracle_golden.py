@@ -75,3 +75,41 @@ def test_model_matches_reference_golden(golden, contracts, name, hw):
     np.testing.assert_allclose(norms, golden[p + "grad_norms"], rtol=2e-3, atol=1e-9)
     assert rel_err(osd["models.encoder.encoder.conv1.weight"].grad, golden[p + "grad_enc_conv1"]) < 2e-3
     assert rel_err(osd["models.encoder.encoder.bn1.running_mean"], golden[p + "bn1_running_mean"]) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["segdec_r50", "pad_r50"])
+def test_seg_decoders_match_reference_golden(golden, contracts, name):
+    """JointSegDepthDecoder / PAD restatements (models/joint_segmentation_depth_decoder.py) + cross_entropy2d."""
+    from helpers import unpack_named_mask
+    H, W, B = 64, 96, 2
+    c = contracts[name]
+    sd = O.synthetic_state_dict({k: torch.empty(s) for k, s in c["state_dict"].items()}, seed=2)
+    osd = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in sd.items()}
+    inputs = O.synthetic_inputs(B, H, W, seed=6, labels=True)
+    p = "seg_%s_" % name
+    mode = O.BNMode(True)
+    feats = O.resnet_features(osd, "models.encoder.encoder.", inputs[("color_aug", 0, 0)], 50, [False, False, True], mode)
+    da = c["cfg"]["depth_args"]
+    if name == "segdec_r50":
+        masks = {"aspp": unpack_named_mask(golden, p + "mask_aspp"), "head": unpack_named_mask(golden, p + "mask_head")}
+        sem = O.joint_seg_depth_decoder(osd, "models.segmentation.", feats, mode=mode, dropout_masks=masks, depth_args=da)
+        loss = O.cross_entropy2d(sem, inputs["lbl"])
+    else:
+        masks = {"depth": unpack_named_mask(golden, p + "mask_depth"), "seg": unpack_named_mask(golden, p + "mask_seg")}
+        out = O.pad_decoder(osd, "models.mtl_decoder.", feats, mode=mode, dropout_masks=masks, depth_args=da)
+        sem = out["semantics"]
+        loss = (O.cross_entropy2d(sem, inputs["lbl"]) + O.cross_entropy2d(out["intermediate_semantics"], inputs["lbl"])) / 2
+        assert rel_err(out["intermediate_semantics"], golden[p + "intermediate"]) < 1e-5
+        for s in range(4):
+            assert rel_err(out[("disp", s)], golden[p + "disp%d" % s]) < 1e-5
+    assert rel_err(sem[:, :, ::4, ::4], golden[p + "semantics"]) < 1e-5
+    assert abs(loss.item() - float(golden[p + "loss"])) < 1e-5 * abs(float(golden[p + "loss"]))
+    loss.backward()
+    names = [str(n) for n in golden[p + "grad_names"]]
+    have = [n for n in names if osd[n].grad is not None]
+    norms = np.array([osd[n].grad.norm().item() for n in have])
+    ref = np.array([golden[p + "grad_norms"][names.index(n)] for n in have])
+    np.testing.assert_allclose(norms, ref, rtol=5e-3, atol=1e-9)
+    # parameters the reference gave a (zero) gradient that the functional oracle never touched must be zero there too
+    rest = [golden[p + "grad_norms"][names.index(n)] for n in names if n not in have]
+    assert all(v == 0 for v in rest), rest[:3]
