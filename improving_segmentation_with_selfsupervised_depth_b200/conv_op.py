@@ -253,9 +253,82 @@ class _StemConvFn(torch.autograd.Function):
         return None, None, dw, None, None
 
 
+class _HeadConvFn(torch.autograd.Function):
+    """C -> 1, 3x3, pad 1 (the sigmoid disparity heads, depth_decoder.py:69-70,107-112) on the tensor cores:
+    z = 1x1conv(x) to 9 tap planes (N padded to 32) + a 9-tap stencil; backward = adjoint stencil of dy (gcol) +
+    two 1x1 GEMMs (dgrad: gcol x Wz, wgrad: x^T x gcol)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, pad_mode, act):
+        A.require_cuda(x, weight)
+        x = ops.as_cl(x)
+        w = ops.ohwi(weight.detach())            # [1][3][3][C] == [9][C]
+        n, c, h, wd = x.shape
+        dev, st = x.device, A.stream_ptr()
+        wz = torch.zeros(32 * c, device=dev, dtype=torch.float32)
+        A.call("segsde_copy_rows", A.ptr(w), C.c_int(c), A.ptr(wz), C.c_int(c), C.c_int(9), C.c_int(c), st)
+        z = ops.cl_empty(n, 32, h, wd, dev)
+        d1 = ops._desc(1, 1, 1, 0, 1, A.PAD_ZERO, False, A.ACT_NONE, False)
+        desc = "head %d->1 k3 out %dx%d (1x1 GEMM + stencil)" % (c, h, wd)
+        _fwd(x, None, wz, None, z, d1, "fprop", 2.0 * n * h * wd * 9 * c, desc)
+        y = ops.cl_empty(n, 1, h, wd, dev)
+        reflect = int(pad_mode == A.PAD_REFLECT)
+        b = bias.detach() if bias is not None else None
+        A.call("segsde_head_stencil_fwd", C.byref(ops.view(z)), C.byref(ops.view(y)), A.ptr(b), C.c_int(act),
+               C.c_int(reflect), C.c_int(1), st)
+        ctx.save_for_backward(x, w, wz, y if act != A.ACT_NONE else None)
+        ctx.cfg = (reflect, act, bias is not None, desc)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, wz, y = ctx.saved_tensors
+        reflect, act, has_bias, desc = ctx.cfg
+        n, c, h, wd = x.shape
+        dev, st = x.device, A.stream_ptr()
+        dy = ops.as_cl(dy)
+        need_x, need_w, need_b = ctx.needs_input_grad[:3]
+        db = torch.zeros(1, device=dev, dtype=torch.float32) if (has_bias and need_b) else None
+        if act != A.ACT_NONE or db is not None:
+            dz = ops.cl_empty(*dy.shape, dev) if act != A.ACT_NONE else None
+            A.call("segsde_act_bwd_bias", ops._ref(ops.view(y)) if y is not None else None, C.byref(ops.view(dy)),
+                   ops._ref(ops.view(dz)) if dz is not None else None, C.c_int(act), A.ptr(db), st)
+            dz = dy if dz is None else dz
+        else:
+            dz = dy
+        dx = dw = None
+        if need_x or need_w:
+            gcol = ops.cl_empty(n, 32, h, wd, dev)
+            A.call("segsde_head_gcol", C.byref(ops.view(dz)), C.byref(ops.view(gcol)), C.c_int(reflect), C.c_int(1), st)
+            d1 = ops._desc(1, 1, 1, 0, 1, A.PAD_ZERO, False, A.ACT_NONE, False)
+            if need_x:
+                wzt = torch.empty(c * 32, device=dev, dtype=torch.float32)
+                A.call("segsde_weight_transpose_flip", A.ptr(wz), A.ptr(wzt), C.c_int(32), C.c_int(1), C.c_int(1),
+                       C.c_int(c), C.c_int(0), C.c_int(c), st)
+                dx = ops.cl_empty(n, c, h, wd, dev)
+                _fwd(gcol, None, wzt, None, dx, d1, "dgrad", 2.0 * n * h * wd * 9 * c, desc)
+            if need_w:
+                dwz = torch.zeros(32 * c, device=dev, dtype=torch.float32)
+                v1, vg = ops.view(x), ops.view(gcol)
+
+                def launch_w():
+                    if A.try_call("segsde_conv2d_wgrad_tc", C.byref(v1), None, C.byref(vg), A.ptr(dwz), None,
+                                  C.byref(d1), st):
+                        return
+                    A.call("segsde_conv2d_wgrad", C.byref(v1), None, C.byref(vg), A.ptr(dwz), None, C.byref(d1), st)
+                ops._timed("wgrad", 2.0 * n * h * wd * 9 * c, launch_w, desc)
+                dw = torch.empty_like(w)
+                A.call("segsde_copy_rows", A.ptr(dwz), C.c_int(c), A.ptr(dw), C.c_int(c), C.c_int(9), C.c_int(c), st)
+        return dx, dw, db, None, None
+
+
 def conv2d(x1, weight, bias=None, x2=None, stride=1, pad=0, dil=1, pad_mode=A.PAD_ZERO, up1=False,
            act=A.ACT_NONE, nchw_norm_in=False):
     """y = act(conv(cat(up?(x1), x2)) + bias) — see segsde_conv2d_fwd / segsde_conv2d_fwd_tc."""
+    if (weight.shape[0] == 1 and tuple(weight.shape[2:]) == (3, 3) and x2 is None and not up1 and stride == 1
+            and pad == 1 and dil == 1 and not nchw_norm_in and weight.shape[1] % 64 == 0 and x1.shape[-1] % 32 == 0
+            and _tc_enabled()):
+        return _HeadConvFn.apply(x1, weight, bias, pad_mode, act)
     if (nchw_norm_in and bias is None and act == A.ACT_NONE and dil == 1 and weight.shape[0] % 64 == 0
             and _tc_enabled()):
         return _StemConvFn.apply(x1, x2, weight, stride, pad)

@@ -146,32 +146,45 @@ extern "C" int segsde_act_bwd_bias(const segsde_nhwc_t* y, const segsde_nhwc_t* 
 // Kpad-channel NHWC tensor and its wgrad is the 1x1 wgrad.
 // ---------------------------------------------------------------------------------------------------
 namespace segsde {
-// one CTA per 32 consecutive output pixels of a row: gather (k, pixel) with pixel-fastest reads (coalesced
-// along the image row), transpose through shared memory, write the 32 x Kpad block contiguously
+// One CTA per 32 consecutive output pixels of a row.  The input patch ([C][kh][32*stride + kw] floats, normalised,
+// zero outside the image) is staged in shared memory with coalesced row reads, a k -> patch-offset table replaces
+// the per-element div/mod, and the 32 x Kpad block leaves through a transposing tile with contiguous writes.
 __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
                                                           int C1, int C2, int N, int H, int W, int kh, int kw, int stride,
                                                           int pad, int Ho, int Wo, int Kpad, float* __restrict__ cols) {
-  extern __shared__ float tile[];                 // [32][Kpad + 1]
+  extern __shared__ float sm[];
+  const int Ct = C1 + C2, K = kh * kw * Ct, ld = Kpad + 1;
+  const int PW = 32 * stride + kw;                 // patch row length
+  float* tile = sm;                                // [32][ld]
+  float* patch = tile + 32 * ld;                   // [Ct][kh][PW]
+  int* lut = reinterpret_cast<int*>(patch + Ct * kh * PW);   // [Kpad]
   const int segs = (Wo + 31) / 32;
   int b = blockIdx.x;
   const int seg = b % segs; b /= segs;
   const int oh = b % Ho; const int n = b / Ho;
   const int ow0 = seg * 32;
-  const int Ct = C1 + C2, K = kh * kw * Ct, ld = Kpad + 1;
+  for (int k = threadIdx.x; k < Kpad; k += blockDim.x) {
+    int v = -1;
+    if (k < K) { const int c = k % Ct, tap = k / Ct, s = tap % kw, r = tap / kw; v = (c * kh + r) * PW + s; }
+    lut[k] = v;
+  }
+  const int w0 = ow0 * stride - pad, h0 = oh * stride - pad;
+  for (int i = threadIdx.x; i < Ct * kh * PW; i += blockDim.x) {
+    const int j = i % PW, cr = i / PW, r = cr % kh, c = cr / kh;
+    const int h = h0 + r, w = w0 + j;
+    float v = 0.f;
+    if (h >= 0 && h < H && w >= 0 && w < W) {
+      const float* src = c < C1 ? x1 + (((long long)n * C1 + c) * H + h) * W + w
+                                : x2 + (((long long)n * C2 + (c - C1)) * H + h) * W + w;
+      v = (__ldg(src) - 0.45f) / 0.225f;
+    }
+    patch[i] = v;
+  }
+  __syncthreads();
   for (int i = threadIdx.x; i < 32 * Kpad; i += blockDim.x) {
     const int px = i & 31, k = i >> 5;
-    float v = 0.f;
-    const int ow = ow0 + px;
-    if (k < K && ow < Wo) {
-      const int c = k % Ct, tap = k / Ct, s = tap % kw, r = tap / kw;
-      const int h = oh * stride - pad + r, w = ow * stride - pad + s;
-      if (h >= 0 && h < H && w >= 0 && w < W) {
-        const float* src = c < C1 ? x1 + (((long long)n * C1 + c) * H + h) * W + w
-                                  : x2 + (((long long)n * C2 + (c - C1)) * H + h) * W + w;
-        v = (__ldg(src) - 0.45f) / 0.225f;
-      }
-    }
-    tile[px * ld + k] = v;
+    const int o = lut[k];
+    tile[px * ld + k] = o >= 0 ? patch[o + px * stride] : 0.f;
   }
   __syncthreads();
   const int npx = min(32, Wo - ow0);
@@ -193,7 +206,10 @@ extern "C" int segsde_stem_im2col(const float* x1, const float* x2, int c1, int 
   if (!x1 || !cols || c1 < 1 || (c2 > 0 && !x2) || kpad < kh * kw * (c1 + c2)) return SEGSDE_E_ARG;
   const int Ho = (h + 2 * pad - kh) / stride + 1, Wo = (w + 2 * pad - kw) / stride + 1;
   const long long blocks = (long long)n * Ho * cdiv(Wo, 32);
-  const size_t smem = sizeof(float) * 32 * (kpad + 1);
+  const size_t smem = sizeof(float) * (32 * (kpad + 1) + (size_t)(c1 + c2) * kh * (32 * stride + kw) + kpad);
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(stem_im2col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; }
+  if (smem > 96 * 1024) return SEGSDE_E_UNSUPPORTED;
   stem_im2col_kernel<<<(unsigned)blocks, 256, smem, as_stream(stream)>>>(x1, x2, c1, c2, n, h, w, kh, kw, stride, pad, Ho, Wo,
                                                                         kpad, cols);
   return launched();

@@ -189,3 +189,93 @@ int c1_wgrad(const View& x, const View& dy, float* dw, const segsde_conv_desc_t*
 }
 
 }  // namespace segsde
+
+// ---------------------------------------------------------------------------------------------------
+// Disparity heads on the tensor cores: a C -> 1 3x3 conv is a 1x1 conv to 9 "tap planes" (z[p][t] = <x[p], w[t]>,
+// a [P x C] x [C x 9] GEMM, N padded to 32) followed by a 9-tap scalar stencil; its backward needs the adjoint
+// stencil of dy (gcol[q][t] = sum of dy over the outputs whose tap t reads q) and two more 1x1 GEMMs.
+// ---------------------------------------------------------------------------------------------------
+namespace segsde {
+
+__global__ void head_stencil_fwd_kernel(View z, View y, const float* __restrict__ bias, int act, int reflect, int pad) {
+  const long long total = (long long)y.n * y.h * y.w;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int w = (int)(idx % y.w); long long q = idx / y.w;
+  const int h = (int)(q % y.h); const int n = (int)(q / y.h);
+  float acc = bias ? bias[0] : 0.f;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    int hh = h - pad + r;
+    if (!c1_resolve(hh, z.h, reflect)) continue;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      int ww = w - pad + s;
+      if (!c1_resolve(ww, z.w, reflect)) continue;
+      acc += __ldg(z.p + z.off(n, hh, ww) + r * 3 + s);
+    }
+  }
+  y.p[y.off(n, h, w)] = act_apply(acc, act);
+}
+
+// gcol[n,h,w,t] = sum over padded-domain preimages (hp,wp) of (h,w) of dy[hp + pad - r, wp + pad - s], t = r*3+s
+__global__ void head_gcol_kernel(View dy, View g, int reflect, int pad) {
+  const long long total = (long long)g.n * g.h * g.w;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int w = (int)(idx % g.w); long long q = idx / g.w;
+  const int h = (int)(q % g.h); const int n = (int)(q / g.h);
+  int rows[3], cols[3]; int nr = 0, nc = 0;
+  rows[nr++] = h; cols[nc++] = w;
+  if (reflect) {
+    if (h >= 1 && h <= pad) rows[nr++] = -h;
+    if (h >= g.h - 1 - pad && h <= g.h - 2) rows[nr++] = 2 * (g.h - 1) - h;
+    if (w >= 1 && w <= pad) cols[nc++] = -w;
+    if (w >= g.w - 1 - pad && w <= g.w - 2) cols[nc++] = 2 * (g.w - 1) - w;
+  }
+  float v[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) v[t] = 0.f;
+  for (int i = 0; i < nr; ++i)
+    for (int j = 0; j < nc; ++j)
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int oh = rows[i] + pad - r;
+        if (oh < 0 || oh >= dy.h) continue;
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const int ow = cols[j] + pad - s;
+          if (ow < 0 || ow >= dy.w) continue;
+          v[r * 3 + s] += __ldg(dy.p + dy.off(n, oh, ow));
+        }
+      }
+  float* o = g.p + g.off(n, h, w);
+  float4* o4 = reinterpret_cast<float4*>(o);
+  o4[0] = make_float4(v[0], v[1], v[2], v[3]);
+  o4[1] = make_float4(v[4], v[5], v[6], v[7]);
+  o4[2] = make_float4(v[8], 0.f, 0.f, 0.f);
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int k = 3; k < 8; ++k) o4[k] = zero;
+}
+
+}  // namespace segsde
+using namespace segsde;
+
+extern "C" int segsde_head_stencil_fwd(const segsde_nhwc_t* z, const segsde_nhwc_t* y, const float* bias, int act,
+                                       int reflect, int pad, void* stream) {
+  if (!z || !y || !z->ptr || !y->ptr || z->c < 9 || y->c != 1 || pad != 1) return SEGSDE_E_ARG;
+  View vz = mk(z), vy = mk(y);
+  if (vz.h != vy.h || vz.w != vy.w || vz.n != vy.n) return SEGSDE_E_ARG;
+  const long long total = (long long)vy.n * vy.h * vy.w;
+  head_stencil_fwd_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(vz, vy, bias, act, reflect, pad);
+  return launched();
+}
+extern "C" int segsde_head_gcol(const segsde_nhwc_t* dy, const segsde_nhwc_t* gcol, int reflect, int pad, void* stream) {
+  if (!dy || !gcol || !dy->ptr || !gcol->ptr || gcol->c != 32 || dy->c != 1 || pad != 1) return SEGSDE_E_ARG;
+  View vd = mk(dy), vg = mk(gcol);
+  if (vd.h != vg.h || vd.w != vg.w || vd.n != vg.n || !vec4_ok(vg)) return SEGSDE_E_ARG;
+  const long long total = (long long)vg.n * vg.h * vg.w;
+  head_gcol_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(vd, vg, reflect, pad);
+  return launched();
+}

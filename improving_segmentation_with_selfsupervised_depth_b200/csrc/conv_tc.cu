@@ -461,13 +461,13 @@ extern "C" int segsde_conv2d_fwd_tc(const segsde_nhwc_t* x1, const segsde_nhwc_t
   if (d->stride != 1 && d->stride != 2) return SEGSDE_E_UNSUPPORTED;   // stride 2 = TMA element strides
   View v1 = mk(x1), v2 = mk(x2), vy = mk(y);
   const int C1 = v1.c, C2 = v2.p ? v2.c : 0, Cout = vy.c;
-  if (C1 % 32 || C2 % 32 || Cout % 64) return SEGSDE_E_UNSUPPORTED;
+  if (C1 % 32 || C2 % 32 || Cout % 32) return SEGSDE_E_UNSUPPORTED;
   if (v2.p && (v2.h != v1.h || v2.w != v1.w || v2.n != v1.n)) return SEGSDE_E_ARG;
   const int Ho = (v1.h + 2 * d->pad - d->dil * (d->kh - 1) - 1) / d->stride + 1;
   const int Wo = (v1.w + 2 * d->pad - d->dil * (d->kw - 1) - 1) / d->stride + 1;
   if (vy.h != Ho || vy.w != Wo || vy.n != v1.n) return SEGSDE_E_ARG;
   if (!vec4_ok(vy)) return SEGSDE_E_UNSUPPORTED;
-  const int BN = (Cout % 128 == 0) ? 128 : 64;
+  const int BN = (Cout % 128 == 0) ? 128 : (Cout % 64 == 0 ? 64 : 32);
   TcConvP p;
   p.y = vy; p.bias = bias; p.act = d->act;
   p.C[0] = C1; p.C[1] = C2; p.Ctot = C1 + C2; p.Cout = Cout;
@@ -482,7 +482,9 @@ extern "C" int segsde_conv2d_fwd_tc(const segsde_nhwc_t* x1, const segsde_nhwc_t
   if (!make_act_map(&a0, v1, p.BW, p.BH, d->stride)) return SEGSDE_E_UNSUPPORTED;
   if (C2) { if (!make_act_map(&a1, v2, p.BW, p.BH, d->stride)) return SEGSDE_E_UNSUPPORTED; } else a1 = a0;
   if (!make_w_map(&b, w, d->kh * d->kw * p.Ctot, Cout, BN)) return SEGSDE_E_UNSUPPORTED;
-  return BN == 128 ? launch_conv<128>(a0, a1, b, p, as_stream(stream)) : launch_conv<64>(a0, a1, b, p, as_stream(stream));
+  if (BN == 128) return launch_conv<128>(a0, a1, b, p, as_stream(stream));
+  if (BN == 64) return launch_conv<64>(a0, a1, b, p, as_stream(stream));
+  return launch_conv<32>(a0, a1, b, p, as_stream(stream));
 }
 
 // dgrad on the tensor cores = fprop of dy with the transposed/tap-flipped weights; the Python layer prepares

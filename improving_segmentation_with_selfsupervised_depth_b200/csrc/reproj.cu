@@ -128,7 +128,7 @@ __device__ __forceinline__ float ssim_from_sums(float sx, float sy, float sxx, f
 }
 
 template <bool GRAD>
-__global__ void __launch_bounds__(NTHREADS) reproj_kernel(ReprojK k) {
+__global__ void __launch_bounds__(NTHREADS, GRAD ? 3 : 4) reproj_kernel(ReprojK k) {
   constexpr int R = GRAD ? 2 : 1;        // halo of the warped images
   constexpr int RC = R - 1;              // halo of the loss centres
   constexpr int RW = TX + 2 * R, RH = TY + 2 * R, NP = RW * RH;

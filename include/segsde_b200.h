@@ -108,6 +108,12 @@ int segsde_act_bwd_bias(const segsde_nhwc_t* y, const segsde_nhwc_t* dy, const s
 int segsde_stem_im2col(const float* x1, const float* x2, int c1, int c2, int n, int h, int w, int kh, int kw,
                        int stride, int pad, int kpad, float* cols, void* stream);
 int segsde_copy_rows(const float* src, int ld_src, float* dst, int ld_dst, int rows, int ncopy, void* stream);
+/* Disparity heads (C -> 1, 3x3, pad 1) on the tensor cores: y = act(bias + sum_t z[resolve(p + tap_t)][t]) over the
+ * 9 tap planes z = 1x1conv(x) (first 9 of >= 9 channels), and the adjoint stencil gcol[q][t] (32 channels, 9 used)
+ * of dy that turns dgrad / wgrad into 1x1 GEMMs. */
+int segsde_head_stencil_fwd(const segsde_nhwc_t* z, const segsde_nhwc_t* y, const float* bias, int act, int reflect,
+                            int pad, void* stream);
+int segsde_head_gcol(const segsde_nhwc_t* dy, const segsde_nhwc_t* gcol, int reflect, int pad, void* stream);
 /* 1 if this process can run the tensor-core path (driver entry point for tensor maps found). */
 int segsde_tc_available(void);
 

@@ -120,3 +120,31 @@ def test_tc_conv_stride2(k, cin, cout, H, W):
     assert rel_err(gy, y) < TOL, "fprop"
     assert rel_err(gx.grad, x.grad) < TOL, "dgrad"
     assert rel_err(gw.grad, w.grad) < TOL, "wgrad"
+
+
+@pytest.mark.parametrize("cin,H,W,reflect", [(64, 16, 32, True), (128, 9, 64, True), (64, 12, 32, False)])
+def test_tc_disparity_head(cin, H, W, reflect):
+    """C -> 1 sigmoid heads through the tap-plane GEMM + stencil route (fwd, dgrad, wgrad, dbias)."""
+    A, ops = _mods()
+    ops.USE_TC = True
+    g = torch.Generator().manual_seed(cin + H)
+    x = torch.randn(2, cin, H, W, generator=g).requires_grad_()
+    w = (torch.randn(1, cin, 3, 3, generator=g) / (cin * 9) ** 0.5).requires_grad_()
+    b = torch.randn(1, generator=g).requires_grad_()
+    y = _ref(x, None, w, b, 1, 1, reflect, False, 3)
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy)
+    gx = x.detach().cuda().requires_grad_()
+    gw = w.detach().cuda().contiguous(memory_format=torch.channels_last).requires_grad_()
+    gb = b.detach().cuda().requires_grad_()
+    ops.PROFILE, ops.PROFILE_DESC = [], []
+    gy = ops.conv2d(gx, gw, gb, pad=1, pad_mode=A.PAD_REFLECT if reflect else A.PAD_ZERO, act=A.ACT_SIGMOID)
+    gy.backward(dy.cuda())
+    torch.cuda.synchronize()
+    descs = list(ops.PROFILE_DESC)
+    ops.PROFILE, ops.PROFILE_DESC = None, None
+    assert any("head" in (d or "") for d in descs)
+    assert rel_err(gy, y) < TOL
+    assert rel_err(gx.grad, x.grad) < TOL
+    assert rel_err(gw.grad, w.grad) < TOL
+    assert rel_err(gb.grad, b.grad) < TOL
