@@ -15,6 +15,7 @@
 // lane), warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> bias/activation -> global).
 // Accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -88,14 +89,72 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 //              1 = SWIZZLE_128B_BASE32B (32-byte atoms, 4-row period) - the only layout tcgen05 accepts for
 //                  MN-major tf32 operands (cutlass sm100_common.inl:92)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                              uint32_t layout_type = 2) {
+                                              uint32_t layout_type = 2, uint32_t base_offset = 0) {
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | ((uint64_t)layout_type << 61);
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | ((uint64_t)(base_offset & 7u) << 49) |
+         ((uint64_t)layout_type << 61);
 }
 // instruction descriptor for kind::tf32, fp32 accumulate, M = 128
 __host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// epilogue activation: ELU through ex2.approx (abs error ~1e-7, far below the TF32 operand rounding of this path)
+__device__ __forceinline__ float act_tc(float v, int act) {
+  if (act == SEGSDE_ACT_ELU) return v > 0.f ? v : __expf(v) - 1.f;
+  if (act == SEGSDE_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == SEGSDE_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
+  return v;
+}
+static int tc_dbg() {   // experiments only: bit0 skip epilogue stores, bit1 skip TMEM loads
+  static int m = -1;
+  if (m < 0) { const char* e = getenv("SEGSDE_TC_DBG"); m = e ? atoi(e) : 0; }
+  return m;
+}
+
+// Epilogue of one 32-row x 32-column accumulator chunk owned by one warp: bias + activation in registers, then a
+// transpose through a padded shared-memory tile so that every st.global.v4 instruction of the warp writes four
+// complete 128-byte lines (the direct form - each lane storing 16 B of its own row - cost 0.5 ms of a 1.5 ms layer).
+// row_ptr(r) returns the output pointer of accumulator row r of this warp (nullptr when the pixel is outside).
+constexpr int EPI_LD = 36;     // floats per staged row: 144 B keeps both the 128-bit writes and reads conflict free
+template <class RowPtr>
+__device__ __forceinline__ void epilogue_chunk(float (&v)[32], const float* __restrict__ bias32, int act,
+                                               float* __restrict__ stage, int lane, RowPtr row_ptr, int col0) {
+  if (bias32) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bias32) + j);
+      v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+    }
+  }
+  switch (act) {
+    case SEGSDE_ACT_ELU:
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : __expf(v[i]) - 1.f;
+      break;
+    case SEGSDE_ACT_RELU:
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+      break;
+    case SEGSDE_ACT_SIGMOID:
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = 1.f / (1.f + __expf(-v[i]));
+      break;
+    default: break;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(stage + lane * EPI_LD + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  __syncwarp();
+  const int c16 = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = (lane >> 3) + 4 * i;
+    float* dst = row_ptr(r);
+    if (dst) *reinterpret_cast<float4*>(dst + col0 + c16 * 4) = *reinterpret_cast<const float4*>(stage + r * EPI_LD + c16 * 4);
+  }
+  __syncwarp();
 }
 
 constexpr int STAGES = 6;
@@ -124,6 +183,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
   __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float epi_stage[4][32 * EPI_LD];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]);
@@ -205,33 +265,24 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int q = warp - 4;                 // TMEM lane quarter
-    const int m = q * 32 + lane;
+    float* stage = epi_stage[q];
     int as = 0; uint32_t aphase = 0;
     for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       const int tn = (int)(t % p.tiles_n); long long qq = t / p.tiles_n;
       const int tw = (int)(qq % p.tiles_w); qq /= p.tiles_w;
       const int th = (int)(qq % p.tiles_h); const int n = (int)(qq / p.tiles_h);
-      const int h = th * p.BH + m / p.BW, w = tw * p.BW + m % p.BW;
-      const bool valid = h < p.Ho && w < p.Wo;
-      float* out = p.y.p + p.y.off(n, valid ? h : 0, valid ? w : 0) + tn * BN;
+      auto row_ptr = [&](int r) -> float* {
+        const int m = q * 32 + r;
+        const int h = th * p.BH + m / p.BW, w = tw * p.BW + m % p.BW;
+        return (h < p.Ho && w < p.Wo) ? p.y.p + p.y.off(n, h, w) + tn * BN : nullptr;
+      };
       mbar_wait(tfull0 + 8 * as, aphase);
       tc_fence_after();
 #pragma unroll 1
       for (int cc = 0; cc < BN / 32; ++cc) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + cc * 32, v);
-        if (valid) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 o;
-            const int c = tn * BN + cc * 32 + j * 4;
-            o.x = act_apply(v[4 * j + 0] + (p.bias ? __ldg(p.bias + c + 0) : 0.f), p.act);
-            o.y = act_apply(v[4 * j + 1] + (p.bias ? __ldg(p.bias + c + 1) : 0.f), p.act);
-            o.z = act_apply(v[4 * j + 2] + (p.bias ? __ldg(p.bias + c + 2) : 0.f), p.act);
-            o.w = act_apply(v[4 * j + 3] + (p.bias ? __ldg(p.bias + c + 3) : 0.f), p.act);
-            *reinterpret_cast<float4*>(out + cc * 32 + j * 4) = o;
-          }
-        }
+        epilogue_chunk(v, p.bias ? p.bias + tn * BN + cc * 32 : nullptr, p.act, stage, lane, row_ptr, cc * 32);
       }
       tc_fence_before();
       __syncwarp();
@@ -244,6 +295,165 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3x3 / stride 1 fprop (and dgrad) with row-halo reuse, for layers at least 128 pixels wide.
+// One CTA tile = 2 output rows x 128 pixels x BN channels (two M=128 accumulators sharing every weight tile).
+// A stage is one (32-channel chunk, tap row r): two input rows are fetched as (128 + 2*dil)-pixel TMA boxes and
+// the three horizontal taps are the SAME shared-memory rows addressed through descriptors whose start is shifted
+// by s*dil*128 B (the 128B swizzle is a function of absolute smem address bits, base offset 0), so an input row is read from L2 3x per tile instead of 9x,
+// and a weight tile 4.5x instead of 9x.  (ncu, round 1: the one-box-per-tap kernel moves 21.7 GB through L2 for a
+// 3.2 GB layer and is L2-bandwidth bound.)
+// ------------------------------------------------------------------------------------------------
+struct TcRowP {
+  View y;
+  const float* bias;
+  int act;
+  int C[2], Ctot, Cout;
+  int pad, dil;
+  int Ho, Wo, N;
+  int tiles_w, tiles_h, tiles_n;     // tiles_h = ceil(Ho / 2)
+  long long total_tiles;
+  int row_bytes;                     // (128 + 2*dil) * 128 rounded up to 1024
+  int base_off_mode;                 // 1: descriptor base_offset = (addr >> 7) & 7 ; 0: always 0
+  int dbg;
+};
+
+template <int BN, int NSTAGE>
+__global__ void __launch_bounds__(NT, 1)
+tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                  const __grid_constant__ CUtensorMap tmB, const TcRowP p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int B_BYTES = BN * 128;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stage_bytes = 2 * p.row_bytes + 3 * B_BYTES;
+  __shared__ __align__(8) uint64_t bars[2 * NSTAGE + 4];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float epi_stage[4][32 * EPI_LD];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[NSTAGE]);
+  const uint32_t tfull0 = smem_u32(&bars[2 * NSTAGE]), tempty0 = smem_u32(&bars[2 * NSTAGE + 2]);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tma_prefetch_desc(&tmA0); tma_prefetch_desc(&tmB);
+    if (p.C[1]) tma_prefetch_desc(&tmA1);
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"(4 * BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  const int kchunks = p.Ctot / 32;
+  const int nstg = kchunks * 3;            // stages per tile
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const uint32_t tx_bytes = 2u * (uint32_t)((128 + 2 * p.dil) * 128) + 3u * B_BYTES;
+      for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const int tn = (int)(t % p.tiles_n); long long q = t / p.tiles_n;
+        const int tw = (int)(q % p.tiles_w); q /= p.tiles_w;
+        const int th = (int)(q % p.tiles_h); const int n = (int)(q / p.tiles_h);
+        const int wi = tw * 128 - p.pad, h0 = th * 2;
+        for (int kc = 0; kc < kchunks; ++kc) {
+          const int c = kc * 32;
+          const bool s0 = c < p.C[0];
+          for (int r = 0; r < 3; ++r) {
+            mbar_wait(empty0 + 8 * stage, phase ^ 1);
+            const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+            const uint32_t sb = sa + 2 * p.row_bytes;
+            const uint32_t fb = full0 + 8 * stage;
+            mbar_expect_tx(fb, tx_bytes);
+            const int hi = h0 - p.pad + r * p.dil;
+            tma_load_4d(sa, s0 ? &tmA0 : &tmA1, fb, s0 ? c : c - p.C[0], wi, hi, n);
+            tma_load_4d(sa + p.row_bytes, s0 ? &tmA0 : &tmA1, fb, s0 ? c : c - p.C[0], wi, hi + 1, n);
+#pragma unroll
+            for (int s = 0; s < 3; ++s) tma_load_2d(sb + s * B_BYTES, &tmB, fb, (r * 3 + s) * p.Ctot + c, tn * BN);
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc(BN, 0, 0);
+    int stage = 0; uint32_t phase = 0;
+    int as = 0; uint32_t aphase = 0;
+    for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      mbar_wait(tempty0 + 8 * as, aphase ^ 1);
+      tc_fence_after();
+      for (int it = 0; it < nstg; ++it) {
+        mbar_wait(full0 + 8 * stage, phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t sb = sa + 2 * p.row_bytes;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const uint32_t d_tmem = tmem_base + (as * 2 + j) * BN;
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+              const uint32_t arow = sa + j * p.row_bytes + s * p.dil * 128;
+              const uint32_t bo = p.base_off_mode ? ((arow >> 7) & 7u) : 0u;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t ad = make_desc(arow + 32 * k, 16, 1024, 2, bo);
+                const uint64_t bd = make_desc(sb + s * B_BYTES + 32 * k, 16, 1024);
+                tc_mma_tf32(d_tmem, ad, bd, idesc, (it | s | k) != 0);
+              }
+            }
+          }
+          tc_commit(empty0 + 8 * stage);
+          if (it == nstg - 1) tc_commit(tfull0 + 8 * as);
+        }
+        __syncwarp();
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+      }
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    float* stage = epi_stage[q];
+    int as = 0; uint32_t aphase = 0;
+    for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const int tn = (int)(t % p.tiles_n); long long qq = t / p.tiles_n;
+      const int tw = (int)(qq % p.tiles_w); qq /= p.tiles_w;
+      const int th = (int)(qq % p.tiles_h); const int n = (int)(qq / p.tiles_h);
+      mbar_wait(tfull0 + 8 * as, aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < 2; ++j) {
+        const int h = th * 2 + j;
+        auto row_ptr = [&](int r) -> float* {
+          const int w = tw * 128 + q * 32 + r;
+          return (h < p.Ho && w < p.Wo) ? p.y.p + p.y.off(n, h, w) + tn * BN : nullptr;
+        };
+#pragma unroll 1
+        for (int cc = 0; cc < BN / 32; ++cc) {
+          float v[32];
+          if (!(p.dbg & 2)) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (as * 2 + j) * BN + cc * 32, v);
+          if (!(p.dbg & 1))
+            epilogue_chunk(v, p.bias ? p.bias + tn * BN + cc * 32 : nullptr, p.act, stage, lane, row_ptr, cc * 32);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * as);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(4 * BN));
   }
 }
 
@@ -443,6 +653,32 @@ static int launch_wgrad(const CUtensorMap& x0, const CUtensorMap& x1, const CUte
   return launched();
 }
 
+template <int BN, int NSTAGE>
+static int launch_conv3x3(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcRowP& p, cudaStream_t st) {
+  const int smem = NSTAGE * (2 * p.row_bytes + 3 * BN * 128) + 1024;
+  static int attr = 0;
+  if (smem > 200 * 1024) return SEGSDE_E_UNSUPPORTED;
+  if (smem > attr) {
+    if (cudaFuncSetAttribute(tc_conv3x3_kernel<BN, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      cudaGetLastError();
+      return SEGSDE_E_UNSUPPORTED;
+    }
+    attr = smem;
+  }
+  long long grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  tc_conv3x3_kernel<BN, NSTAGE><<<(int)grid, NT, smem, st>>>(a0, a1, b, p);
+  return launched();
+}
+
+// SEGSDE_TC_ROWHALO: 0 = off, 2 (default) = on, descriptor base_offset 0, 1 = on with base_offset = (addr>>7)&7.
+// Measured on B200: the swizzle XOR is taken from the absolute shared-memory address bits, so a start address
+// shifted by whole 128-byte rows needs base_offset 0 (mode 1 produces wrong results; kept for the record).
+static int rowhalo_mode() {
+  static int m = -1;
+  if (m < 0) { const char* e = getenv("SEGSDE_TC_ROWHALO"); m = e ? atoi(e) : 2; }
+  return m;
+}
+
 static int pow2_floor(int v) { int r = 1; while (r * 2 <= v) r *= 2; return r; }
 
 }  // namespace segsde
@@ -479,6 +715,22 @@ extern "C" int segsde_conv2d_fwd_tc(const segsde_nhwc_t* x1, const segsde_nhwc_t
   p.tiles_w = cdiv(Wo, p.BW); p.tiles_h = cdiv(Ho, p.BH); p.tiles_n = Cout / BN;
   p.total_tiles = (long long)p.tiles_w * p.tiles_h * p.N * p.tiles_n;
   CUtensorMap a0, a1, b;
+  if (rowhalo_mode() && d->kh == 3 && d->kw == 3 && d->stride == 1 && Wo >= 128 && BN >= 64 && 128 + 2 * d->dil <= 256) {
+    TcRowP r;
+    r.y = vy; r.bias = bias; r.act = d->act; r.C[0] = C1; r.C[1] = C2; r.Ctot = C1 + C2; r.Cout = Cout;
+    r.pad = d->pad; r.dil = d->dil; r.Ho = Ho; r.Wo = Wo; r.N = v1.n;
+    r.tiles_w = cdiv(Wo, 128); r.tiles_h = cdiv(Ho, 2); r.tiles_n = Cout / BN;
+    r.total_tiles = (long long)r.tiles_w * r.tiles_h * r.N * r.tiles_n;
+    r.row_bytes = (((128 + 2 * d->dil) * 128) + 1023) / 1024 * 1024;
+    r.base_off_mode = rowhalo_mode() == 1;
+    r.dbg = tc_dbg();
+    if (make_act_map(&a0, v1, 128 + 2 * d->dil, 1, 1) && (!C2 || make_act_map(&a1, v2, 128 + 2 * d->dil, 1, 1)) &&
+        make_w_map(&b, w, 9 * r.Ctot, Cout, BN)) {
+      if (!C2) a1 = a0;
+      return BN == 128 ? launch_conv3x3<128, 2>(a0, a1, b, r, as_stream(stream))
+                       : launch_conv3x3<64, 3>(a0, a1, b, r, as_stream(stream));
+    }
+  }
   if (!make_act_map(&a0, v1, p.BW, p.BH, d->stride)) return SEGSDE_E_UNSUPPORTED;
   if (C2) { if (!make_act_map(&a1, v2, p.BW, p.BH, d->stride)) return SEGSDE_E_UNSUPPORTED; } else a1 = a0;
   if (!make_w_map(&b, w, d->kh * d->kw * p.Ctot, Cout, BN)) return SEGSDE_E_UNSUPPORTED;

@@ -41,6 +41,11 @@ CASES = [
     (64, 64, 64, 3, 1, 1, True, False, 2, True, 1, 32, 64),
     (256, 0, 192, 1, 0, 1, False, False, 0, False, 2, 9, 13),
     (96, 0, 256, 3, 1, 1, False, False, 0, False, 1, 20, 160),
+    # >= 128 pixels wide: row-halo kernel (2 output rows per tile, shifted-descriptor taps)
+    (64, 64, 64, 3, 1, 1, True, False, 2, True, 1, 6, 256),
+    (32, 32, 128, 3, 1, 1, True, True, 2, True, 2, 5, 64),
+    (64, 0, 64, 3, 2, 2, False, False, 0, False, 1, 7, 160),
+    (64, 0, 128, 3, 1, 1, False, False, 0, True, 2, 9, 130),
 ]
 
 
