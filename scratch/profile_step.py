@@ -41,5 +41,5 @@ print('--- convs (kind, desc, ms, TF/s)')
 rows = []
 for (kind, fl, a, b), d in zip(ops.PROFILE, ops.PROFILE_DESC):
     ms = a.elapsed_time(b); rows.append((ms, kind, d, fl / (ms * 1e-3 + 1e-12) / 1e12))
-for ms, kind, d, tf in sorted(rows, key=lambda r: -r[0])[:45]:
+for ms, kind, d, tf in sorted(rows, key=lambda r: -r[0])[:70]:
     print('%7.2f ms %-6s %-44s %7.1f TF/s' % (ms, kind, d, tf))
