@@ -213,11 +213,29 @@ def run_b200(args):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         last = None
-        for _ in range(nsteps):
-            if e2e:
-                inputs = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        if e2e:
+            # every step's inputs travel pinned host -> device inside the timed region; the copy of step i+1 is
+            # issued on a side stream while step i computes (double buffering), the loss is read back every step
+            copy_stream = torch.cuda.Stream(device=dev)
+            main = torch.cuda.current_stream()
+
+            def upload():
+                with torch.cuda.stream(copy_stream):
+                    bufs = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+                    ev = torch.cuda.Event()
+                    ev.record(copy_stream)
+                return bufs, ev
+            nxt = upload()
+            for i in range(nsteps):
+                inputs, ev = nxt
+                main.wait_event(ev)
+                if i + 1 < nsteps:
+                    nxt = upload()
+                for v in inputs.values():
+                    v.record_stream(main)
                 last = step(inputs).item()          # D2H read of the step's loss
-            else:
+        else:
+            for _ in range(nsteps):
                 last = step(resident)
         ev1.record()
         barrier()
@@ -236,10 +254,12 @@ def run_b200(args):
         clocks.start()
     # instrument every convolution launch with CUDA events during the timed region
     ops.PROFILE = []
+    A.PROFILE, A.PROFILE_NAMES = [], {"segsde_reproj_fused"}
     n0 = A.launch_count()
     ms, last = timed(args.steps, e2e=False)
     launches = A.launch_count() - n0
     prof, ops.PROFILE = ops.PROFILE, None
+    rprof, A.PROFILE, A.PROFILE_NAMES = A.PROFILE, None, None
     ms_e2e, last_e2e = timed(args.steps, e2e=True)
     clk = clocks.stop() if rank == 0 else None
     if rank != 0:
@@ -270,6 +290,15 @@ def run_b200(args):
             "by_kind": {k: {"tflops": v[0] / (v[1] * 1e-3 + 1e-12) / 1e12, "ms_per_step": v[1] / args.steps,
                             "launches_per_step": v[2] / args.steps} for k, v in fam.items()}}
 
+    # ---- the HBM-bound kernel of the path: fused reprojection + SSIM + L1 + auto-mask (+ gradients) ---------------
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    r_ms = sum(e0.elapsed_time(e1) for _, e0, e1 in rprof) or 1.0
+    r_bytes = args.steps * sum(B * (4 * 9 * H * W + 4 * (H >> s) * (W >> s)) for s in range(4))
+    roof_hbm = {"kernel": "reproj_kernel<GRAD> (4 launches per step, one per scale)", "bound": "hbm",
+                "achieved": r_bytes / (r_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": r_bytes / (r_ms * 1e-3) / 1e9 / hbm_peak, "ms_per_step": r_ms / args.steps,
+                "traffic": 273.3e6, "traffic_source": "ncu --set full, scale-0 launch, B=12: dram read 265.5 MB + write 11.9 MB "
+                                                      "(profiles/r1_hot_kernels.md); instruction-bound, not HBM-bound"}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         import torch as _t
@@ -295,7 +324,7 @@ def run_b200(args):
                    "train_gflop_per_image": FWD_GF_TRAIN_PER_SAMPLE},
         "e2e": {"value": gb * args.steps / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+        "gpu_launches": launches, "clocks": clk, "roofline": roof, "roofline_hbm_kernel": roof_hbm, "cpu_baseline": cpu,
         "loss": float(last), "conv_roofline_frac_whole_step": FWD_GF_TRAIN_PER_SAMPLE * 1e9 * gb * args.steps
         / (ms * 1e-3) / 1e12 / peak_tf / world,
     }

@@ -69,11 +69,12 @@ def check(code, what=""):
 
 # when a list, every entry-point call is bracketed by CUDA events: (name, ev0, ev1) — profiling scripts only
 PROFILE = None
+PROFILE_NAMES = None      # optional set: only these entry points are bracketed
 
 
 def _invoke(name, args):
     fn = getattr(lib(), name)
-    if PROFILE is None:
+    if PROFILE is None or (PROFILE_NAMES is not None and name not in PROFILE_NAMES):
         return fn(*args)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

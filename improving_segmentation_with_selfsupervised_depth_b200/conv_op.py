@@ -36,23 +36,29 @@ def _prep(x, up, pad):
     return y
 
 
-def _fwd(x1, x2, w, b, y, d, kind, flops, desc=None):
+def _fwd(x1, x2, w, b, y, d, kind, flops, desc=None, stats=None):
+    """stats: optional [tensor(3C, float64, zero-filled), done-flag] box — BatchNorm batch statistics of y are
+    accumulated by the tensor-core epilogue when that route is taken (done-flag set), else left to the caller."""
     st = A.stream_ptr()
     v1, v2, vy = ops.view(x1), (ops.view(x2) if x2 is not None else None), ops.view(y)
     if d.nchw_norm_in:
         v1.sn = v1.sh = v1.sw = 0
 
     def launch():
-        if _tc_enabled() and A.try_call("segsde_conv2d_fwd_tc", C.byref(v1), ops._ref(v2), A.ptr(w), A.ptr(b),
-                                        C.byref(vy), C.byref(d), st):
-            return
+        if _tc_enabled():
+            if stats is not None and A.try_call("segsde_conv2d_fwd_tc_stats", C.byref(v1), ops._ref(v2), A.ptr(w), A.ptr(b),
+                                                C.byref(vy), C.byref(d), A.ptr(stats[0]), st):
+                stats[1] = True
+                return
+            if A.try_call("segsde_conv2d_fwd_tc", C.byref(v1), ops._ref(v2), A.ptr(w), A.ptr(b), C.byref(vy), C.byref(d), st):
+                return
         A.call("segsde_conv2d_fwd", C.byref(v1), ops._ref(v2), A.ptr(w), A.ptr(b), C.byref(vy), C.byref(d), st)
     ops._timed(kind, flops, launch, desc)
 
 
 class _Conv2dFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x1, x2, weight, bias, stride, pad, dil, pad_mode, up1, act, nchw):
+    def forward(ctx, x1, x2, weight, bias, stride, pad, dil, pad_mode, up1, act, nchw, stats=None):
         A.require_cuda(x1, weight)
         if nchw:
             x1 = x1.contiguous()
@@ -86,7 +92,7 @@ class _Conv2dFn(torch.autograd.Function):
         b = bias.detach() if bias is not None else None
         desc = "%d+%d->%d k%d s%d d%d out %dx%d%s%s" % (c1, c2, cout, kh, stride, dil, ho, wo,
                                                         " prep" if prepped else "", " sub2" if sub2 else "")
-        _fwd(x1e, x2e, w, b, y, d, "fprop", 2.0 * n * ho * wo * cout * kh * kw * ctot, desc)
+        _fwd(x1e, x2e, w, b, y, d, "fprop", 2.0 * n * ho * wo * cout * kh * kw * ctot, desc, stats)
         ctx.save_for_backward(x1e, x2e, w, y if act != A.ACT_NONE else None)
         ctx.cfg = (stride, pad, dil, pad_mode, up1, act, nchw, bias is not None, prepped, pad_e, mode_e, up_e,
                    tuple(x1.shape), tuple(x2.shape) if x2 is not None else None, sub2, full_shape1, tc_ch)
@@ -196,7 +202,7 @@ class _Conv2dFn(torch.autograd.Function):
                     return
                 A.call("segsde_conv2d_wgrad", C.byref(v1), ops._ref(v2), C.byref(vdz), A.ptr(dw), None, C.byref(d), st)
             ops._timed("wgrad", flops_scale * 2.0 * nz * hz * wz * cout * kh * kw * ctot, launch_w, ctx.desc)
-        return dx1, dx2, dw, db, None, None, None, None, None, None, None
+        return dx1, dx2, dw, db, None, None, None, None, None, None, None, None
 
 
 class _StemConvFn(torch.autograd.Function):
@@ -204,7 +210,7 @@ class _StemConvFn(torch.autograd.Function):
     normalisation (x-0.45)/0.225 happens inside the im2col pass.  Only the weight gets a gradient."""
 
     @staticmethod
-    def forward(ctx, x1, x2, weight, stride, pad):
+    def forward(ctx, x1, x2, weight, stride, pad, stats=None):
         A.require_cuda(x1, weight)
         x1 = x1.contiguous().float()
         x2 = x2.contiguous().float() if x2 is not None else None
@@ -224,7 +230,7 @@ class _StemConvFn(torch.autograd.Function):
         y = ops.cl_empty(n, cout, ho, wo, x1.device)
         d = ops._desc(1, 1, 1, 0, 1, A.PAD_ZERO, False, A.ACT_NONE, False)
         desc = "stem %d+%d->%d k%d s%d out %dx%d im2col" % (c1, c2, cout, kh, stride, ho, wo)
-        _fwd(cols, None, wpad, None, y, d, "fprop", 2.0 * n * ho * wo * cout * k, desc)
+        _fwd(cols, None, wpad, None, y, d, "fprop", 2.0 * n * ho * wo * cout * k, desc, stats)
         ctx.save_for_backward(cols, w)
         ctx.cfg = (k, kpad, desc)
         return y
@@ -234,7 +240,7 @@ class _StemConvFn(torch.autograd.Function):
         cols, w = ctx.saved_tensors
         k, kpad, desc = ctx.cfg
         if not ctx.needs_input_grad[2]:
-            return None, None, None, None, None
+            return None, None, None, None, None, None
         cout = w.shape[0]
         dy = ops.as_cl(dy)
         st = A.stream_ptr()
@@ -250,7 +256,7 @@ class _StemConvFn(torch.autograd.Function):
         ops._timed("wgrad", 2.0 * n * ho * wo * cout * k, launch_w, desc)
         dw = torch.empty_like(w)
         A.call("segsde_copy_rows", A.ptr(dwp), C.c_int(kpad), A.ptr(dw), C.c_int(k), C.c_int(cout), C.c_int(k), st)
-        return None, None, dw, None, None
+        return None, None, dw, None, None, None
 
 
 class _HeadConvFn(torch.autograd.Function):
@@ -323,8 +329,19 @@ class _HeadConvFn(torch.autograd.Function):
 
 
 def conv2d(x1, weight, bias=None, x2=None, stride=1, pad=0, dil=1, pad_mode=A.PAD_ZERO, up1=False,
-           act=A.ACT_NONE, nchw_norm_in=False):
-    """y = act(conv(cat(up?(x1), x2)) + bias) — see segsde_conv2d_fwd / segsde_conv2d_fwd_tc."""
+           act=A.ACT_NONE, nchw_norm_in=False, bn_stats=None):
+    """y = act(conv(cat(up?(x1), x2)) + bias) — see segsde_conv2d_fwd / segsde_conv2d_fwd_tc.
+    bn_stats: optional zero-filled float64 tensor [3*Cout]; on return it holds the BatchNorm batch statistics of y
+    (sum, sum of squares, shift) — from the convolution epilogue when possible, else from segsde_bn_stats."""
+    if bn_stats is not None:
+        box = [bn_stats, False]
+        if (nchw_norm_in and bias is None and act == A.ACT_NONE and dil == 1 and weight.shape[0] % 64 == 0 and _tc_enabled()):
+            y = _StemConvFn.apply(x1, x2, weight, stride, pad, box)
+        else:
+            y = _Conv2dFn.apply(x1, x2, weight, bias, stride, pad, dil, pad_mode, up1, act, nchw_norm_in, box)
+        if not box[1]:
+            A.call("segsde_bn_stats", C.byref(ops.view(y.detach())), A.ptr(bn_stats), A.stream_ptr())
+        return y
     if (weight.shape[0] == 1 and tuple(weight.shape[2:]) == (3, 3) and x2 is None and not up1 and stride == 1
             and pad == 1 and dil == 1 and not nchw_norm_in and weight.shape[1] % 64 == 0 and x1.shape[-1] % 32 == 0
             and _tc_enabled()):

@@ -118,9 +118,12 @@ static int tc_dbg() {   // experiments only: bit0 skip epilogue stores, bit1 ski
 // complete 128-byte lines (the direct form - each lane storing 16 B of its own row - cost 0.5 ms of a 1.5 ms layer).
 // row_ptr(r) returns the output pointer of accumulator row r of this warp (nullptr when the pixel is outside).
 constexpr int EPI_LD = 36;     // floats per staged row: 144 B keeps both the 128-bit writes and reads conflict free
+// csum (nullable): CTA-level shared accumulators [2][Cout] of sum / sum of squares per output channel (BatchNorm
+// batch statistics fused into the producing convolution); csum_c = first channel of this chunk.
 template <class RowPtr>
 __device__ __forceinline__ void epilogue_chunk(float (&v)[32], const float* __restrict__ bias32, int act,
-                                               float* __restrict__ stage, int lane, RowPtr row_ptr, int col0) {
+                                               float* __restrict__ stage, int lane, RowPtr row_ptr, int col0,
+                                               float* __restrict__ csum = nullptr, int csum_c = 0, int cout = 0) {
   if (bias32) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -154,10 +157,21 @@ __device__ __forceinline__ void epilogue_chunk(float (&v)[32], const float* __re
     float* dst = row_ptr(r);
     if (dst) *reinterpret_cast<float4*>(dst + col0 + c16 * 4) = *reinterpret_cast<const float4*>(stage + r * EPI_LD + c16 * 4);
   }
+  if (csum) {      // lane = channel: sum the staged column over the rows that are real pixels
+    const unsigned valid = __ballot_sync(0xffffffffu, row_ptr(lane) != nullptr);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+      if (valid & (1u << r)) { const float t = stage[r * EPI_LD + lane]; s1 += t; s2 = fmaf(t, t, s2); }
+    }
+    atomicAdd(csum + csum_c + lane, s1);
+    atomicAdd(csum + cout + csum_c + lane, s2);
+  }
   __syncwarp();
 }
 
-constexpr int STAGES = 6;
+constexpr int STAGES = 5;
+constexpr int MAX_STAT_C = 2048;
 constexpr int A_BYTES = 128 * 128;        // 128 rows x 32 fp32
 constexpr int NT = 256;
 
@@ -171,6 +185,7 @@ struct TcConvP {
   int Ho, Wo, N;
   int BW, BH, tiles_w, tiles_h, tiles_n;   // pixel tile = BW x BH (=128), tiles_n = Cout / BN
   long long total_tiles;
+  double* stats;              // nullable: [0,C) += sum y, [C,2C) += sum y^2 (BatchNorm statistics of the output)
 };
 
 template <int BN>
@@ -184,6 +199,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float epi_stage[4][32 * EPI_LD];
+  __shared__ float csum[2 * MAX_STAT_C];
+  if (p.stats) for (int i = threadIdx.x; i < 2 * p.Cout; i += blockDim.x) csum[i] = 0.f;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]);
@@ -282,7 +299,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       for (int cc = 0; cc < BN / 32; ++cc) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + cc * 32, v);
-        epilogue_chunk(v, p.bias ? p.bias + tn * BN + cc * 32 : nullptr, p.act, stage, lane, row_ptr, cc * 32);
+        epilogue_chunk(v, p.bias ? p.bias + tn * BN + cc * 32 : nullptr, p.act, stage, lane, row_ptr, cc * 32,
+                       p.stats ? csum : nullptr, tn * BN + cc * 32, p.Cout);
       }
       tc_fence_before();
       __syncwarp();
@@ -292,6 +310,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  if (p.stats) for (int i = threadIdx.x; i < 2 * p.Cout; i += blockDim.x) atomicAdd(p.stats + i, (double)csum[i]);
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN));
@@ -319,6 +338,7 @@ struct TcRowP {
   int row_bytes;                     // (128 + 2*dil) * 128 rounded up to 1024
   int base_off_mode;                 // 1: descriptor base_offset = (addr >> 7) & 7 ; 0: always 0
   int dbg;
+  double* stats;
 };
 
 template <int BN, int NSTAGE>
@@ -332,6 +352,8 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   __shared__ __align__(8) uint64_t bars[2 * NSTAGE + 4];
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float epi_stage[4][32 * EPI_LD];
+  __shared__ float csum[2 * MAX_STAT_C];
+  if (p.stats) for (int i = threadIdx.x; i < 2 * p.Cout; i += blockDim.x) csum[i] = 0.f;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[NSTAGE]);
   const uint32_t tfull0 = smem_u32(&bars[2 * NSTAGE]), tempty0 = smem_u32(&bars[2 * NSTAGE + 2]);
@@ -440,7 +462,8 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           float v[32];
           if (!(p.dbg & 2)) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (as * 2 + j) * BN + cc * 32, v);
           if (!(p.dbg & 1))
-            epilogue_chunk(v, p.bias ? p.bias + tn * BN + cc * 32 : nullptr, p.act, stage, lane, row_ptr, cc * 32);
+            epilogue_chunk(v, p.bias ? p.bias + tn * BN + cc * 32 : nullptr, p.act, stage, lane, row_ptr, cc * 32,
+                           p.stats ? csum : nullptr, tn * BN + cc * 32, p.Cout);
         }
       }
       tc_fence_before();
@@ -451,6 +474,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
+  if (p.stats) for (int i = threadIdx.x; i < 2 * p.Cout; i += blockDim.x) atomicAdd(p.stats + i, (double)csum[i]);
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(4 * BN));
@@ -837,10 +861,21 @@ extern "C" int segsde_tc_available(void) { return tc_init() ? 1 : 0; }
 
 // y = act(conv(cat(x1, x2), w) + bias), zero padding, stride 1 or 2, any dilation; channel counts multiples
 // of 32 (inputs) / 64 (outputs).  Anything else -> SEGSDE_E_UNSUPPORTED (caller uses the generic path).
+extern "C" int segsde_conv2d_fwd_tc_stats(const segsde_nhwc_t* x1, const segsde_nhwc_t* x2, const float* w,
+                                          const float* bias, const segsde_nhwc_t* y, const segsde_conv_desc_t* d,
+                                          double* stats, void* stream);
 extern "C" int segsde_conv2d_fwd_tc(const segsde_nhwc_t* x1, const segsde_nhwc_t* x2, const float* w,
                                     const float* bias, const segsde_nhwc_t* y, const segsde_conv_desc_t* d,
                                     void* stream) {
+  return segsde_conv2d_fwd_tc_stats(x1, x2, w, bias, y, d, nullptr, stream);
+}
+// Same, and additionally accumulates the per-channel sum / sum of squares of the (pre-activation) output into
+// stats[0..C) / stats[C..2C) (fp64, zero-filled by the caller): BatchNorm batch statistics without a second pass.
+extern "C" int segsde_conv2d_fwd_tc_stats(const segsde_nhwc_t* x1, const segsde_nhwc_t* x2, const float* w,
+                                          const float* bias, const segsde_nhwc_t* y, const segsde_conv_desc_t* d,
+                                          double* stats, void* stream) {
   if (!x1 || !x1->ptr || !w || !y || !y->ptr || !d) return SEGSDE_E_ARG;
+  if (stats && (y->c > MAX_STAT_C || d->act != SEGSDE_ACT_NONE)) return SEGSDE_E_UNSUPPORTED;
   if (!tc_init()) return SEGSDE_E_UNSUPPORTED;
   if (d->pad_mode != SEGSDE_PAD_ZERO || d->up1 || d->nchw_norm_in) return SEGSDE_E_UNSUPPORTED;
   if (d->stride != 1 && d->stride != 2) return SEGSDE_E_UNSUPPORTED;   // stride 2 = TMA element strides
@@ -854,7 +889,7 @@ extern "C" int segsde_conv2d_fwd_tc(const segsde_nhwc_t* x1, const segsde_nhwc_t
   if (!vec4_ok(vy)) return SEGSDE_E_UNSUPPORTED;
   const int BN = (Cout % 128 == 0) ? 128 : (Cout % 64 == 0 ? 64 : 32);
   TcConvP p;
-  p.y = vy; p.bias = bias; p.act = d->act;
+  p.y = vy; p.bias = bias; p.act = d->act; p.stats = stats;
   p.C[0] = C1; p.C[1] = C2; p.Ctot = C1 + C2; p.Cout = Cout;
   p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pad = d->pad; p.dil = d->dil;
   p.Ho = Ho; p.Wo = Wo; p.N = v1.n;
@@ -873,6 +908,7 @@ extern "C" int segsde_conv2d_fwd_tc(const segsde_nhwc_t* x1, const segsde_nhwc_t
     r.row_bytes = (((128 + 2 * d->dil) * 128) + 1023) / 1024 * 1024;
     r.base_off_mode = rowhalo_mode() == 1;
     r.dbg = tc_dbg();
+    r.stats = stats;
     if (make_act_map(&a0, v1, 128 + 2 * d->dil, 1, 1) && (!C2 || make_act_map(&a1, v2, 128 + 2 * d->dil, 1, 1)) &&
         make_w_map(&b, w, 9 * r.Ctot, Cout, BN)) {
       if (!C2) a1 = a0;

@@ -21,10 +21,11 @@ class Conv2d(nn.Conv2d):
         with torch.no_grad():
             self.weight.data = self.weight.data.contiguous(memory_format=torch.channels_last)
 
-    def forward(self, x, x2=None, up1=False, act=A.ACT_NONE, pad=None, pad_mode=A.PAD_ZERO, nchw_norm_in=False):
+    def forward(self, x, x2=None, up1=False, act=A.ACT_NONE, pad=None, pad_mode=A.PAD_ZERO, nchw_norm_in=False,
+                bn_stats=None):
         return ops.conv2d(x, self.weight, self.bias, x2=x2, stride=self.stride[0],
                           pad=self.padding[0] if pad is None else pad, dil=self.dilation[0], pad_mode=pad_mode,
-                          up1=up1, act=act, nchw_norm_in=nchw_norm_in)
+                          up1=up1, act=act, nchw_norm_in=nchw_norm_in, bn_stats=bn_stats)
 
 
 class BatchNorm2d(nn.BatchNorm2d):
@@ -34,7 +35,10 @@ class BatchNorm2d(nn.BatchNorm2d):
         super().__init__(*args, **kwargs)
         self._pending_batches = 0     # num_batches_tracked is flushed lazily (no per-step tiny kernel)
 
-    def forward(self, x, residual=None, act=A.ACT_NONE):
+    def uses_batch_stats(self):
+        return self.training or not self.track_running_stats
+
+    def forward(self, x, residual=None, act=A.ACT_NONE, sums=None):
         use_batch_stats = self.training or not self.track_running_stats
         update = self.training and self.track_running_stats
         momentum = self.momentum
@@ -47,7 +51,7 @@ class BatchNorm2d(nn.BatchNorm2d):
         else:
             rm, rv = self.running_mean, self.running_var
         return ops.batch_norm(x, self.weight, self.bias, rm, rv, use_batch_stats, momentum or 0.0, self.eps,
-                              residual=residual, act=act)
+                              residual=residual, act=act, sums=sums if use_batch_stats else None)
 
     def _flush(self):
         if self._pending_batches and self.num_batches_tracked is not None:
@@ -61,6 +65,15 @@ class BatchNorm2d(nn.BatchNorm2d):
     def _load_from_state_dict(self, *args, **kwargs):
         self._pending_batches = 0
         super()._load_from_state_dict(*args, **kwargs)
+
+
+def conv_bn(conv, bn, x, residual=None, act=A.ACT_NONE, **conv_kw):
+    """bn(conv(x)) [+ residual] [ReLU] with the BatchNorm batch statistics accumulated in the convolution's
+    tensor-core epilogue (no separate pass over the conv output) when the BN layer normalises with batch statistics."""
+    if isinstance(bn, BatchNorm2d) and bn.uses_batch_stats() and isinstance(conv, Conv2d) and conv.bias is None:
+        sums = torch.zeros(3 * conv.out_channels, device=conv.weight.device, dtype=torch.float64)
+        return bn(conv(x, bn_stats=sums, **conv_kw), residual=residual, act=act, sums=sums)
+    return bn(conv(x, **conv_kw), residual=residual, act=act)
 
 
 class Dropout(nn.Dropout):

@@ -6,7 +6,7 @@ from torch import nn
 
 from .. import _cabi as A
 from .. import ops
-from .layers import BatchNorm2d, Conv2d, Dropout
+from .layers import BatchNorm2d, Conv2d, Dropout, conv_bn
 
 
 class ASPPConv(nn.Sequential):
@@ -15,7 +15,7 @@ class ASPPConv(nn.Sequential):
                          BatchNorm2d(out_channels), nn.ReLU())
 
     def forward(self, x):
-        return self[1](self[0](x), act=A.ACT_RELU)
+        return conv_bn(self[0], self[1], x, act=A.ACT_RELU)
 
 
 class ASPPPooling(nn.Sequential):
@@ -45,10 +45,10 @@ class ASPP(nn.Module):
 
     def forward(self, x):
         first = self.convs[0]
-        res = [first[1](first[0](x), act=A.ACT_RELU)]
+        res = [conv_bn(first[0], first[1], x, act=A.ACT_RELU)]
         for conv in list(self.convs)[1:]:
             res.append(conv(x))
-        y = self.project[1](self.project[0](ops.cat_channels(res)), act=A.ACT_RELU)
+        y = conv_bn(self.project[0], self.project[1], ops.cat_channels(res), act=A.ACT_RELU)
         return self.project[3](y)
 
 

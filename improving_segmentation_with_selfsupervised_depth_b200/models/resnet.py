@@ -6,7 +6,7 @@ from the kernel-backed layers.  Restates what the reference obtains from `torchv
 from torch import nn
 
 from .. import _cabi as A
-from .layers import BatchNorm2d, Conv2d
+from .layers import BatchNorm2d, Conv2d, conv_bn
 
 
 class BasicBlock(nn.Module):
@@ -26,10 +26,10 @@ class BasicBlock(nn.Module):
 
     def forward(self, x):
         identity = x
-        out = self.bn1(self.conv1(x), act=A.ACT_RELU)
+        out = conv_bn(self.conv1, self.bn1, x, act=A.ACT_RELU)
         if self.downsample is not None:
-            identity = self.downsample[1](self.downsample[0](x))
-        return self.bn2(self.conv2(out), residual=identity, act=A.ACT_RELU)
+            identity = conv_bn(self.downsample[0], self.downsample[1], x)
+        return conv_bn(self.conv2, self.bn2, out, residual=identity, act=A.ACT_RELU)
 
 
 class Bottleneck(nn.Module):
@@ -49,11 +49,11 @@ class Bottleneck(nn.Module):
 
     def forward(self, x):
         identity = x
-        out = self.bn1(self.conv1(x), act=A.ACT_RELU)
-        out = self.bn2(self.conv2(out), act=A.ACT_RELU)
+        out = conv_bn(self.conv1, self.bn1, x, act=A.ACT_RELU)
+        out = conv_bn(self.conv2, self.bn2, out, act=A.ACT_RELU)
         if self.downsample is not None:
-            identity = self.downsample[1](self.downsample[0](x))
-        return self.bn3(self.conv3(out), residual=identity, act=A.ACT_RELU)
+            identity = conv_bn(self.downsample[0], self.downsample[1], x)
+        return conv_bn(self.conv3, self.bn3, out, residual=identity, act=A.ACT_RELU)
 
 
 CONFIGS = {18: (BasicBlock, [2, 2, 2, 2]), 34: (BasicBlock, [3, 4, 6, 3]), 50: (Bottleneck, [3, 4, 6, 3]),

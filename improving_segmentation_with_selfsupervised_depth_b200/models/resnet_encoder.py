@@ -5,6 +5,7 @@ from torch import nn
 
 from .. import _cabi as A
 from .. import ops
+from .layers import conv_bn
 from .resnet import CONFIGS, ResNet
 
 
@@ -38,9 +39,12 @@ class ResnetEncoder(nn.Module):
         if num_layers > 34:
             self.num_ch_enc[1:] *= 4
 
-    def _trunk(self, stem):
+    def _trunk(self, first, second=None):
         e = self.encoder
-        self.features = [e.bn1(stem, act=A.ACT_RELU)]
+        kw = {"nchw_norm_in": True}
+        if second is not None:
+            kw["x2"] = second
+        self.features = [conv_bn(e.conv1, e.bn1, first, act=A.ACT_RELU, **kw)]
         x = ops.maxpool3x3s2(self.features[-1])
         for layer in (e.layer1, e.layer2, e.layer3, e.layer4):
             for blk in layer:
@@ -51,10 +55,10 @@ class ResnetEncoder(nn.Module):
     def forward(self, input_image):
         # (x - 0.45) / 0.225 is applied inside the stem kernel while it reads the NCHW image
         A.require_cuda(input_image)
-        return self._trunk(self.encoder.conv1(input_image.float(), nchw_norm_in=True))
+        return self._trunk(input_image.float())
 
     def forward_pair(self, first, second):
         """Stem over the channel concat of two frames without materialising the concat
         (joint_segmentation_depth.py:44: `torch.cat(pose_inputs, 1)`)."""
         A.require_cuda(first, second)
-        return self._trunk(self.encoder.conv1(first.float(), x2=second.float(), nchw_norm_in=True))
+        return self._trunk(first.float(), second.float())

@@ -202,7 +202,7 @@ def conv2d(x1, weight, bias=None, x2=None, stride=1, pad=0, dil=1, pad_mode=A.PA
 # -------------------------------------------------------------------------------------------------
 class _BatchNormFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, running_mean, running_var, training, momentum, eps, act):
+    def forward(ctx, x, weight, bias, residual, running_mean, running_var, training, momentum, eps, act, sums=None):
         x = as_cl(x)
         residual = as_cl(residual) if residual is not None else None
         n, c, h, w = x.shape
@@ -210,8 +210,9 @@ class _BatchNormFn(torch.autograd.Function):
         mean = torch.empty(c, device=dev, dtype=torch.float32)
         invstd = torch.empty(c, device=dev, dtype=torch.float32)
         if training:
-            sums = torch.zeros(3 * c, device=dev, dtype=torch.float64)
-            A.call("segsde_bn_stats", C.byref(view(x)), A.ptr(sums), st)
+            if sums is None:       # not already produced by the convolution epilogue
+                sums = torch.zeros(3 * c, device=dev, dtype=torch.float64)
+                A.call("segsde_bn_stats", C.byref(view(x)), A.ptr(sums), st)
             A.call("segsde_bn_finalize", A.ptr(sums), C.c_int(c), C.c_int64(n * h * w), C.c_float(eps),
                    C.c_float(momentum), A.ptr(mean), A.ptr(invstd), A.ptr(running_mean), A.ptr(running_var), st)
         else:
@@ -246,15 +247,15 @@ class _BatchNormFn(torch.autograd.Function):
                A.ptr(gw), C.c_int(act), C.c_int(1 if training else 0), A.ptr(red), C.c_int64(n * h * w),
                _ref(view(dx)) if dx is not None else None, _ref(view(dres)) if dres is not None else None,
                A.ptr(dgamma), A.ptr(dbeta), st)
-        return dx, dgamma, dbeta, dres, None, None, None, None, None, None
+        return dx, dgamma, dbeta, dres, None, None, None, None, None, None, None
 
 
 def batch_norm(x, weight, bias, running_mean, running_var, training, momentum=0.1, eps=1e-5, residual=None,
-               act=A.ACT_NONE):
+               act=A.ACT_NONE, sums=None):
     """training=True: batch statistics (running buffers, when given, are updated in place);
     training=False: normalise with the running buffers."""
     return _BatchNormFn.apply(x, weight, bias, residual, running_mean, running_var, bool(training),
-                              0.0 if momentum is None else momentum, eps, act)
+                              0.0 if momentum is None else momentum, eps, act, sums)
 
 
 # -------------------------------------------------------------------------------------------------

@@ -85,6 +85,11 @@ int segsde_conv2d_wgrad(const segsde_nhwc_t* x1, const segsde_nhwc_t* x2, const 
 int segsde_conv2d_fwd_tc(const segsde_nhwc_t* x1, const segsde_nhwc_t* x2, const float* w,
                          const float* bias, const segsde_nhwc_t* y, const segsde_conv_desc_t* d,
                          void* stream);
+/* fwd_tc that also accumulates the BatchNorm batch statistics of its (pre-activation) output in the epilogue:
+ * stats[0..C) += sum y, stats[C..2C) += sum y^2 (fp64, zero-filled by the caller; same layout as segsde_bn_stats
+ * with shift 0, consumed by segsde_bn_finalize).  stats == NULL behaves like segsde_conv2d_fwd_tc. */
+int segsde_conv2d_fwd_tc_stats(const segsde_nhwc_t* x1, const segsde_nhwc_t* x2, const float* w, const float* bias,
+                               const segsde_nhwc_t* y, const segsde_conv_desc_t* d, double* stats, void* stream);
 int segsde_conv2d_dgrad_tc(const segsde_nhwc_t* dy, const float* w, const segsde_nhwc_t* dx1,
                            const segsde_nhwc_t* dx2, const segsde_conv_desc_t* d, void* stream);
 int segsde_conv2d_wgrad_tc(const segsde_nhwc_t* x1, const segsde_nhwc_t* x2,
