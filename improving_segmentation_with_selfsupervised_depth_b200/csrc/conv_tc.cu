@@ -526,9 +526,10 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant_
   const uint32_t tmem_base = tmem_base_slot;
 
   // work item: (mt, nt, split)
+  // M-tile fastest, pixel range slowest: CTAs sharing a pixel range are co-scheduled (x / dY served from L2)
   int b = blockIdx.x;
-  const int split = b % p.splits; b /= p.splits;
-  const int nt = b % p.ntiles; const int mt = b / p.ntiles;
+  const int mt = b % p.mtiles; b /= p.mtiles;
+  const int nt = b % p.ntiles; const int split = b / p.ntiles;
   const long long c_beg = (long long)split * p.chunks_per_split;
   const long long c_end = min(p.chunks, c_beg + p.chunks_per_split);
   const int niter = (int)max(0LL, c_end - c_beg);
@@ -656,10 +657,12 @@ tc_wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
+  // tap row fastest, then channel group / output tile, pixel range slowest: the CTAs that stream the same pixels
+  // (x and dY) are co-scheduled, so those tensors come from L2 instead of being re-read from DRAM per tap row
   int b = blockIdx.x;
-  const int split = b % p.splits; b /= p.splits;
-  const int nt = b % p.ntiles; b /= p.ntiles;
-  const int r = b % 3; const int grp = b / 3;
+  const int r = b % 3; b /= 3;
+  const int grp = b % p.groups; b /= p.groups;
+  const int nt = b % p.ntiles; const int split = b / p.ntiles;
   const int src = grp < p.groups0 ? 0 : 1;
   const int cbase = (src ? grp - p.groups0 : grp) * 128;           // within the source
   const int ng = min(4, (p.C[src] - cbase) / 32);                  // valid 32-channel chunks in this group

@@ -1,6 +1,8 @@
 """nn.Module shells around the sm_100a kernels.  They subclass the torch modules the reference uses
 (so `isinstance(m, nn.BatchNorm2d)` checks such as train.py:433-440 keep working and the
 state_dict keys / OIHW shapes are identical) but never call torch compute ops."""
+import os
+
 import torch
 from torch import nn
 
@@ -70,7 +72,8 @@ class BatchNorm2d(nn.BatchNorm2d):
 def conv_bn(conv, bn, x, residual=None, act=A.ACT_NONE, **conv_kw):
     """bn(conv(x)) [+ residual] [ReLU] with the BatchNorm batch statistics accumulated in the convolution's
     tensor-core epilogue (no separate pass over the conv output) when the BN layer normalises with batch statistics."""
-    if isinstance(bn, BatchNorm2d) and bn.uses_batch_stats() and isinstance(conv, Conv2d) and conv.bias is None:
+    if (isinstance(bn, BatchNorm2d) and bn.uses_batch_stats() and isinstance(conv, Conv2d) and conv.bias is None
+            and os.environ.get("SEGSDE_NO_BNFUSE", "0") != "1"):
         sums = torch.zeros(3 * conv.out_channels, device=conv.weight.device, dtype=torch.float64)
         return bn(conv(x, bn_stats=sums, **conv_kw), residual=residual, act=act, sums=sums)
     return bn(conv(x, **conv_kw), residual=residual, act=act)
