@@ -189,7 +189,9 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
   __syncthreads();
   const int npx = min(32, Wo - ow0);
   float* dst = cols + (((long long)n * Ho + oh) * Wo + ow0) * Kpad;
-  for (int i = threadIdx.x; i < npx * Kpad; i += blockDim.x) dst[i] = tile[(i / Kpad) * ld + (i % Kpad)];
+  // one warp per pixel row: contiguous 128-byte segments, no integer division
+  for (int px = threadIdx.x >> 5; px < npx; px += blockDim.x >> 5)
+    for (int k = threadIdx.x & 31; k < Kpad; k += 32) dst[(long long)px * Kpad + k] = tile[px * ld + k];
 }
 // dst[r][0..cols_dst) = src[r][0..cols_src) zero-padded / truncated (row-major)
 __global__ void copy_rows_kernel(const float* __restrict__ src, int ld_src, float* __restrict__ dst, int ld_dst,

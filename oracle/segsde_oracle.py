@@ -170,7 +170,7 @@ def rot_from_axisangle(vec):
     ]
     B = vec.shape[0]
     top = torch.stack([torch.stack([e.reshape(B) for e in r], 1) for r in rows], 1)   # B,3,3
-    R = torch.zeros(B, 4, 4)
+    R = torch.zeros(B, 4, 4, device=vec.device)
     R[:, :3, :3] = top
     R[:, 3, 3] = 1
     return R
@@ -184,8 +184,8 @@ def transformation_from_parameters(axisangle, translation, invert=False):
         R = R.transpose(1, 2)
         t = -t
     B = t.shape[0]
-    Tm = torch.cat([torch.cat([torch.eye(3).expand(B, 3, 3), t], 2),
-                    torch.tensor([0., 0., 0., 1.]).expand(B, 1, 4)], 1)
+    Tm = torch.cat([torch.cat([torch.eye(3, device=t.device).expand(B, 3, 3), t], 2),
+                    torch.tensor([0., 0., 0., 1.], device=t.device).expand(B, 1, 4)], 1)
     return torch.matmul(R, Tm) if invert else torch.matmul(Tm, R)
 
 
