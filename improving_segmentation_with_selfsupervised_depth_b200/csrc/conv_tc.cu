@@ -11,8 +11,10 @@
 //       both operands MN-major straight out of NHWC (pixels are the GEMM-K), split over pixel ranges,
 //       partial sums reduced with red.global.add.f32.
 //
-// Warp roles (256 threads, 1 CTA / SM, persistent): warp 0 = TMA producer, warp 1 = MMA issuer (one elected
-// lane), warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> bias/activation -> global).
+// Warp roles (1 CTA / SM, persistent): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warp 2 = TMEM
+// allocator, warps 4.. = epilogue (TMEM -> registers -> bias/activation -> smem transpose -> global): eight of them
+// in the fprop/dgrad kernels (384 threads; a single warp per SM sub-partition ran the epilogue latency-bound at
+// ~2.3 TB/s of output, measured on the 64->256 1x1 layers), four in the wgrad kernels (256 threads).
 // Accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda.h>
 #include <stdlib.h>
@@ -83,6 +85,27 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// Split form for software pipelining: issue the load of the next accumulator chunk, work on the current one, then
+// wait.  The wait names all 32 registers as read-write operands so the compiler cannot move a use above it.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+        "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+        "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+        "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+      :: "memory");
+}
 
 // shared-memory matrix descriptor, SWIZZLE_128B (cute::UMMA::SmemDescriptor: version 1, layout type 2)
 // layout_type: 2 = SWIZZLE_128B (16-byte swizzle atoms, 8-row period; K-major operands),
@@ -116,14 +139,16 @@ static int tc_dbg() {   // experiments only: bit0 skip epilogue stores, bit1 ski
 // Epilogue of one 32-row x 32-column accumulator chunk owned by one warp: bias + activation in registers, then a
 // transpose through a padded shared-memory tile so that every st.global.v4 instruction of the warp writes four
 // complete 128-byte lines (the direct form - each lane storing 16 B of its own row - cost 0.5 ms of a 1.5 ms layer).
-// row_ptr(r) returns the output pointer of accumulator row r of this warp (nullptr when the pixel is outside).
+// dst8[i] = output pointer (first channel of the CTA's N tile) of accumulator row (lane>>3) + 4*i of this warp,
+// nullptr when that pixel is outside the image; valid = ballot of "row `lane` is a real pixel".  Both are computed
+// once per tile by the caller (the div/mod of the pixel decomposition stays out of the per-chunk path).
 constexpr int EPI_LD = 36;     // floats per staged row: 144 B keeps both the 128-bit writes and reads conflict free
 // csum (nullable): CTA-level shared accumulators [2][Cout] of sum / sum of squares per output channel (BatchNorm
 // batch statistics fused into the producing convolution); csum_c = first channel of this chunk.
-template <class RowPtr>
 __device__ __forceinline__ void epilogue_chunk(float (&v)[32], const float* __restrict__ bias32, int act,
-                                               float* __restrict__ stage, int lane, RowPtr row_ptr, int col0,
-                                               float* __restrict__ csum = nullptr, int csum_c = 0, int cout = 0) {
+                                               float* __restrict__ stage, int lane, float* const (&dst8)[8], int col0,
+                                               unsigned valid, float* __restrict__ csum = nullptr, int csum_c = 0,
+                                               int cout = 0) {
   if (bias32) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -154,26 +179,62 @@ __device__ __forceinline__ void epilogue_chunk(float (&v)[32], const float* __re
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int r = (lane >> 3) + 4 * i;
-    float* dst = row_ptr(r);
-    if (dst) *reinterpret_cast<float4*>(dst + col0 + c16 * 4) = *reinterpret_cast<const float4*>(stage + r * EPI_LD + c16 * 4);
+    if (dst8[i]) *reinterpret_cast<float4*>(dst8[i] + col0 + c16 * 4) = *reinterpret_cast<const float4*>(stage + r * EPI_LD + c16 * 4);
   }
   if (csum) {      // lane = channel: sum the staged column over the rows that are real pixels
-    const unsigned valid = __ballot_sync(0xffffffffu, row_ptr(lane) != nullptr);
-    float s1 = 0.f, s2 = 0.f;
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};     // four independent chains
+    if (valid == 0xffffffffu) {
 #pragma unroll
-    for (int r = 0; r < 32; ++r) {
-      if (valid & (1u << r)) { const float t = stage[r * EPI_LD + lane]; s1 += t; s2 = fmaf(t, t, s2); }
+      for (int r = 0; r < 32; ++r) { const float t = stage[r * EPI_LD + lane]; s1[r & 3] += t; s2[r & 3] = fmaf(t, t, s2[r & 3]); }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 32; ++r) {
+        if (valid & (1u << r)) { const float t = stage[r * EPI_LD + lane]; s1[r & 3] += t; s2[r & 3] = fmaf(t, t, s2[r & 3]); }
+      }
     }
-    atomicAdd(csum + csum_c + lane, s1);
-    atomicAdd(csum + cout + csum_c + lane, s2);
+    atomicAdd(csum + csum_c + lane, (s1[0] + s1[1]) + (s1[2] + s1[3]));
+    atomicAdd(csum + cout + csum_c + lane, (s2[0] + s2[1]) + (s2[2] + s2[3]));
   }
   __syncwarp();
+}
+
+// One warp's share of a tile's epilogue: chunks first, first + step, ... < nch (32 accumulator columns each) with the
+// TMEM load of the next chunk in flight while the current one is activated / staged / stored.
+template <int MAXI>
+__device__ __forceinline__ void epilogue_chunks(uint32_t taddr0, int first, int step, int nch, const float* bias, int act,
+                                                float* __restrict__ stage, int lane, float* const (&dst8)[8],
+                                                unsigned valid, float* __restrict__ csum, int csum_c0, int cout) {
+  uint32_t ra[32], rb[32];
+  if (first < nch) tmem_ld32_issue(taddr0 + first * 32, ra);
+#pragma unroll
+  for (int i = 0; i < MAXI; ++i) {
+    const int cc = first + i * step;
+    if (cc < nch) {
+      float v[32];
+      if (i & 1) {
+        tmem_ld32_wait(rb);
+        if (cc + step < nch) tmem_ld32_issue(taddr0 + (cc + step) * 32, ra);
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(rb[k]);
+      } else {
+        tmem_ld32_wait(ra);
+        if (cc + step < nch) tmem_ld32_issue(taddr0 + (cc + step) * 32, rb);
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(ra[k]);
+      }
+      epilogue_chunk(v, bias ? bias + cc * 32 : nullptr, act, stage, lane, dst8, cc * 32, valid, csum, csum_c0 + cc * 32, cout);
+    }
+  }
 }
 
 constexpr int STAGES = 5;
 constexpr int MAX_STAT_C = 2048;
 constexpr int A_BYTES = 128 * 128;        // 128 rows x 32 fp32
-constexpr int NT = 256;
+constexpr int NT = 256;                   // wgrad kernels: 4 epilogue warps
+constexpr int NT_CONV = 384;              // fprop / dgrad kernels: 8 epilogue warps (two per TMEM lane quarter)
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_LD * 4;
+constexpr int MAX_DYN_SMEM = 226 * 1024;         // 227 KB per CTA minus the 1 KB of static barriers / slots
 
 struct TcConvP {
   View y;                     // output view
@@ -189,7 +250,7 @@ struct TcConvP {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __launch_bounds__(NT_CONV, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, const TcConvP p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -198,8 +259,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ __align__(16) float epi_stage[4][32 * EPI_LD];
-  __shared__ float csum[2 * MAX_STAT_C];
+  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);      // [EPI_WARPS][32 * EPI_LD]
+  float* csum = epi_stage + EPI_WARPS * 32 * EPI_LD;                             // [2][Cout] when p.stats
   if (p.stats) for (int i = threadIdx.x; i < 2 * p.Cout; i += blockDim.x) csum[i] = 0.f;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -208,7 +269,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&tmA0); tma_prefetch_desc(&tmB);
     if (p.C[1]) tma_prefetch_desc(&tmA1);
@@ -281,8 +342,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int q = warp - 4;                 // TMEM lane quarter
-    float* stage = epi_stage[q];
+    const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int half = (warp - 4) >> 2;       // the two warps of a quarter take alternate 32-column chunks
+    float* stage = epi_stage + (warp - 4) * 32 * EPI_LD;
     int as = 0; uint32_t aphase = 0;
     for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       const int tn = (int)(t % p.tiles_n); long long qq = t / p.tiles_n;
@@ -293,15 +355,15 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int h = th * p.BH + m / p.BW, w = tw * p.BW + m % p.BW;
         return (h < p.Ho && w < p.Wo) ? p.y.p + p.y.off(n, h, w) + tn * BN : nullptr;
       };
+      float* dst8[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dst8[i] = row_ptr((lane >> 3) + 4 * i);
+      const unsigned valid = __ballot_sync(0xffffffffu, row_ptr(lane) != nullptr);
       mbar_wait(tfull0 + 8 * as, aphase);
       tc_fence_after();
-#pragma unroll 1
-      for (int cc = 0; cc < BN / 32; ++cc) {
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + cc * 32, v);
-        epilogue_chunk(v, p.bias ? p.bias + tn * BN + cc * 32 : nullptr, p.act, stage, lane, row_ptr, cc * 32,
-                       p.stats ? csum : nullptr, tn * BN + cc * 32, p.Cout);
-      }
+      epilogue_chunks<(BN / 32 + 1) / 2>(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN, half, 2, BN / 32,
+                                         p.bias ? p.bias + tn * BN : nullptr, p.act, stage, lane, dst8, valid,
+                                         p.stats ? csum : nullptr, tn * BN, p.Cout);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * as);
@@ -342,7 +404,7 @@ struct TcRowP {
 };
 
 template <int BN, int NSTAGE>
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __launch_bounds__(NT_CONV, 1)
 tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmB, const TcRowP p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -351,15 +413,15 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   const int stage_bytes = 2 * p.row_bytes + 3 * B_BYTES;
   __shared__ __align__(8) uint64_t bars[2 * NSTAGE + 4];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ __align__(16) float epi_stage[4][32 * EPI_LD];
-  __shared__ float csum[2 * MAX_STAT_C];
+  float* epi_stage = reinterpret_cast<float*>(smem + (size_t)NSTAGE * stage_bytes);   // [EPI_WARPS][32 * EPI_LD]
+  float* csum = epi_stage + EPI_WARPS * 32 * EPI_LD;                                   // [2][Cout] when p.stats
   if (p.stats) for (int i = threadIdx.x; i < 2 * p.Cout; i += blockDim.x) csum[i] = 0.f;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[NSTAGE]);
   const uint32_t tfull0 = smem_u32(&bars[2 * NSTAGE]), tempty0 = smem_u32(&bars[2 * NSTAGE + 2]);
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&tmA0); tma_prefetch_desc(&tmB);
     if (p.C[1]) tma_prefetch_desc(&tmA1);
@@ -441,31 +503,28 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   } else if (warp >= 4) {
-    const int q = warp - 4;
-    float* stage = epi_stage[q];
+    const int q = warp & 3;                 // TMEM lane quarter
+    const int j = (warp - 4) >> 2;          // output row of the tile this warp writes
+    float* stage = epi_stage + (warp - 4) * 32 * EPI_LD;
     int as = 0; uint32_t aphase = 0;
     for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       const int tn = (int)(t % p.tiles_n); long long qq = t / p.tiles_n;
       const int tw = (int)(qq % p.tiles_w); qq /= p.tiles_w;
       const int th = (int)(qq % p.tiles_h); const int n = (int)(qq / p.tiles_h);
+      const int h = th * 2 + j;
+      auto row_ptr = [&](int r) -> float* {
+        const int w = tw * 128 + q * 32 + r;
+        return (h < p.Ho && w < p.Wo) ? p.y.p + p.y.off(n, h, w) + tn * BN : nullptr;
+      };
+      float* dst8[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dst8[i] = row_ptr((lane >> 3) + 4 * i);
+      const unsigned valid = __ballot_sync(0xffffffffu, row_ptr(lane) != nullptr);
       mbar_wait(tfull0 + 8 * as, aphase);
       tc_fence_after();
-#pragma unroll 1
-      for (int j = 0; j < 2; ++j) {
-        const int h = th * 2 + j;
-        auto row_ptr = [&](int r) -> float* {
-          const int w = tw * 128 + q * 32 + r;
-          return (h < p.Ho && w < p.Wo) ? p.y.p + p.y.off(n, h, w) + tn * BN : nullptr;
-        };
-#pragma unroll 1
-        for (int cc = 0; cc < BN / 32; ++cc) {
-          float v[32];
-          if (!(p.dbg & 2)) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (as * 2 + j) * BN + cc * 32, v);
-          if (!(p.dbg & 1))
-            epilogue_chunk(v, p.bias ? p.bias + tn * BN + cc * 32 : nullptr, p.act, stage, lane, row_ptr, cc * 32,
-                           p.stats ? csum : nullptr, tn * BN + cc * 32, p.Cout);
-        }
-      }
+      epilogue_chunks<BN / 32>(tmem_base + ((uint32_t)(q * 32) << 16) + (as * 2 + j) * BN, 0, 1, BN / 32,
+                               p.bias ? p.bias + tn * BN : nullptr, p.act, stage, lane, dst8, valid,
+                               p.stats ? csum : nullptr, tn * BN, p.Cout);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * as);
@@ -792,11 +851,18 @@ static int num_sms() {
 
 template <int BN>
 static int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcConvP& p, cudaStream_t st) {
-  constexpr int smem = STAGES * (A_BYTES + BN * 128) + 1024;
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(tc_conv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+  const int smem = STAGES * (A_BYTES + BN * 128) + 1024 + EPI_BYTES + (p.stats ? 2 * p.Cout * 4 : 0);
+  static int attr = 0;
+  if (smem > MAX_DYN_SMEM) return SEGSDE_E_UNSUPPORTED;
+  if (smem > attr) {
+    if (cudaFuncSetAttribute(tc_conv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      cudaGetLastError();
+      return SEGSDE_E_UNSUPPORTED;
+    }
+    attr = smem;
+  }
   long long grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  tc_conv_kernel<BN><<<(int)grid, NT, smem, st>>>(a0, a1, b, p);
+  tc_conv_kernel<BN><<<(int)grid, NT_CONV, smem, st>>>(a0, a1, b, p);
   return launched();
 }
 template <int BN>
@@ -810,9 +876,9 @@ static int launch_wgrad(const CUtensorMap& x0, const CUtensorMap& x1, const CUte
 
 template <int BN, int NSTAGE>
 static int launch_conv3x3(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcRowP& p, cudaStream_t st) {
-  const int smem = NSTAGE * (2 * p.row_bytes + 3 * BN * 128) + 1024;
+  const int smem = NSTAGE * (2 * p.row_bytes + 3 * BN * 128) + 1024 + EPI_BYTES + (p.stats ? 2 * p.Cout * 4 : 0);
   static int attr = 0;
-  if (smem > 200 * 1024) return SEGSDE_E_UNSUPPORTED;
+  if (smem > MAX_DYN_SMEM) return SEGSDE_E_UNSUPPORTED;
   if (smem > attr) {
     if (cudaFuncSetAttribute(tc_conv3x3_kernel<BN, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       cudaGetLastError();
@@ -821,7 +887,7 @@ static int launch_conv3x3(const CUtensorMap& a0, const CUtensorMap& a1, const CU
     attr = smem;
   }
   long long grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  tc_conv3x3_kernel<BN, NSTAGE><<<(int)grid, NT, smem, st>>>(a0, a1, b, p);
+  tc_conv3x3_kernel<BN, NSTAGE><<<(int)grid, NT_CONV, smem, st>>>(a0, a1, b, p);
   return launched();
 }
 
