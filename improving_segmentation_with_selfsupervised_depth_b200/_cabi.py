@@ -24,7 +24,7 @@ class NHWC(C.Structure):
 class ConvDesc(C.Structure):
     _fields_ = [("kh", C.c_int32), ("kw", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
                 ("dil", C.c_int32), ("pad_mode", C.c_int32), ("up1", C.c_int32), ("act", C.c_int32),
-                ("nchw_norm_in", C.c_int32)]
+                ("nchw_norm_in", C.c_int32), ("stride_w", C.c_int32)]
 
 
 class ReprojArgs(C.Structure):

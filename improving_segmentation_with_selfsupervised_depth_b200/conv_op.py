@@ -14,6 +14,7 @@ Tensor-core route, by input-side fusion:
   * dgrad everywhere = the fprop kernel on dy with the transposed / tap-flipped weights.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -205,9 +206,21 @@ class _Conv2dFn(torch.autograd.Function):
         return dx1, dx2, dw, db, None, None, None, None, None, None, None, None
 
 
+def _band_view(xp, n, hp, wo, wp, P):
+    """The overlapping row-band view of a segsde_stem_pack buffer: pixel (y, ox) exposes the 8*P contiguous floats
+    that start at padded pixel (y, 2*ox) — c = 8*P, horizontal stride 2*P floats (include/segsde_b200.h)."""
+    v = A.NHWC()
+    v.ptr = xp.data_ptr()
+    v.n, v.h, v.w, v.c = n, hp, wo, 8 * P
+    v.sn, v.sh, v.sw = hp * wp * P, wp * P, 2 * P
+    return v
+
+
 class _StemConvFn(torch.autograd.Function):
-    """7x7/s2 stem on NCHW frames (resnet_encoder.py:92-93) as im2col + tensor-core 1x1 GEMM; the input
-    normalisation (x-0.45)/0.225 happens inside the im2col pass.  Only the weight gets a gradient."""
+    """7x7/s2 stem on NCHW frames (resnet_encoder.py:92-93) on the tensor cores; the input normalisation
+    (x-0.45)/0.225 happens inside the packing pass.  Only the weight gets a gradient.
+    Route 1 ("band"): zero-haloed NHWC-4/8 copy of the frames + a (7 x 1)-tap implicit GEMM over the overlapping
+    row-band view (K = 7*8*P) — the frames are read once.  Route 2 (fallback for odd sizes): im2col + 1x1 GEMM."""
 
     @staticmethod
     def forward(ctx, x1, x2, weight, stride, pad, stats=None):
@@ -219,42 +232,82 @@ class _StemConvFn(torch.autograd.Function):
         n, c1, h, wd = x1.shape
         c2 = x2.shape[1] if x2 is not None else 0
         k = kh * kw * ctot
-        kpad = (k + 31) // 32 * 32
         ho, wo = ops._conv_out_hw(h, wd, kh, kw, stride, pad, 1)
         st = A.stream_ptr()
-        cols = ops.cl_empty(n, kpad, ho, wo, x1.device)
+        dev = x1.device
+        y = ops.cl_empty(n, cout, ho, wo, dev)
+        flops = 2.0 * n * ho * wo * cout * k
+        if (kh == 7 and kw == 7 and stride == 2 and pad == 3 and h % 2 == 0 and wd % 2 == 0 and ctot <= 8
+                and wo % 32 == 0 and cout % 32 == 0 and os.environ.get("SEGSDE_STEM_BAND", "1") != "0"):
+            P = 4 if ctot <= 4 else 8
+            wp = wd + 8
+            xp = torch.empty(n * (h + 6) * wp * P, device=dev, dtype=torch.float32)
+            A.call("segsde_stem_pack", A.ptr(x1), A.ptr(x2), C.c_int(c1), C.c_int(c2), C.c_int(n), C.c_int(h), C.c_int(wd),
+                   C.c_int(3), C.c_int(wp), C.c_int(P), A.ptr(xp), st)
+            wpk = torch.empty(cout * kh * 8 * P, device=dev, dtype=torch.float32)
+            A.call("segsde_stem_pack_w", A.ptr(w), A.ptr(wpk), C.c_int(cout), C.c_int(kh), C.c_int(kw), C.c_int(ctot),
+                   C.c_int(P), C.c_int(0), st)
+            band, vy = _band_view(xp, n, h + 6, wo, wp, P), ops.view(y)
+            d = ops._desc(kh, 1, 2, 0, 1, A.PAD_ZERO, False, A.ACT_NONE, False, stride_w=1)
+            desc = "stem %d+%d->%d k%d s%d out %dx%d band" % (c1, c2, cout, kh, stride, ho, wo)
+            done = []
+
+            def launch():
+                if stats is not None and A.try_call("segsde_conv2d_fwd_tc_stats", C.byref(band), None, A.ptr(wpk), None,
+                                                    C.byref(vy), C.byref(d), A.ptr(stats[0]), st):
+                    stats[1] = True
+                    done.append(1)
+                elif A.try_call("segsde_conv2d_fwd_tc", C.byref(band), None, A.ptr(wpk), None, C.byref(vy), C.byref(d), st):
+                    done.append(1)
+            ops._timed("fprop", flops, launch, desc)
+            if done:
+                ctx.save_for_backward(xp, w)
+                ctx.cfg = ("band", (n, h + 6, wo, wp, P, kh, kw, ctot), flops, desc)
+                return y
+        kpad = (k + 31) // 32 * 32
+        cols = ops.cl_empty(n, kpad, ho, wo, dev)
         A.call("segsde_stem_im2col", A.ptr(x1), A.ptr(x2), C.c_int(c1), C.c_int(c2), C.c_int(n), C.c_int(h), C.c_int(wd),
                C.c_int(kh), C.c_int(kw), C.c_int(stride), C.c_int(pad), C.c_int(kpad), A.ptr(cols), st)
-        wpad = torch.empty(cout * kpad, device=x1.device, dtype=torch.float32)
+        wpad = torch.empty(cout * kpad, device=dev, dtype=torch.float32)
         A.call("segsde_copy_rows", A.ptr(w), C.c_int(k), A.ptr(wpad), C.c_int(kpad), C.c_int(cout), C.c_int(k), st)
-        y = ops.cl_empty(n, cout, ho, wo, x1.device)
         d = ops._desc(1, 1, 1, 0, 1, A.PAD_ZERO, False, A.ACT_NONE, False)
         desc = "stem %d+%d->%d k%d s%d out %dx%d im2col" % (c1, c2, cout, kh, stride, ho, wo)
-        _fwd(cols, None, wpad, None, y, d, "fprop", 2.0 * n * ho * wo * cout * k, desc, stats)
+        _fwd(cols, None, wpad, None, y, d, "fprop", flops, desc, stats)
         ctx.save_for_backward(cols, w)
-        ctx.cfg = (k, kpad, desc)
+        ctx.cfg = ("im2col", (k, kpad), flops, desc)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        cols, w = ctx.saved_tensors
-        k, kpad, desc = ctx.cfg
+        src, w = ctx.saved_tensors
+        mode, geo, flops, desc = ctx.cfg
         if not ctx.needs_input_grad[2]:
             return None, None, None, None, None, None
         cout = w.shape[0]
         dy = ops.as_cl(dy)
         st = A.stream_ptr()
-        n, _, ho, wo = dy.shape
+        vdz = ops.view(dy)
+        dw = torch.empty_like(w)
+        if mode == "band":
+            n, hp, wo, wp, P, kh, kw, ctot = geo
+            band = _band_view(src, n, hp, wo, wp, P)
+            dwp = torch.zeros(cout * kh * 8 * P, device=dy.device, dtype=torch.float32)
+            d = ops._desc(kh, 1, 2, 0, 1, A.PAD_ZERO, False, A.ACT_NONE, False, stride_w=1)
+            ops._timed("wgrad", flops, lambda: A.call("segsde_conv2d_wgrad_tc", C.byref(band), None, C.byref(vdz), A.ptr(dwp),
+                                                      None, C.byref(d), st), desc)
+            A.call("segsde_stem_pack_w", A.ptr(dw), A.ptr(dwp), C.c_int(cout), C.c_int(kh), C.c_int(kw), C.c_int(ctot),
+                   C.c_int(P), C.c_int(1), st)
+            return None, None, dw, None, None, None
+        k, kpad = geo
         dwp = torch.zeros(cout * kpad, device=dy.device, dtype=torch.float32)
         d = ops._desc(1, 1, 1, 0, 1, A.PAD_ZERO, False, A.ACT_NONE, False)
-        v1, vdz = ops.view(cols), ops.view(dy)
+        v1 = ops.view(src)
 
         def launch_w():
             if A.try_call("segsde_conv2d_wgrad_tc", C.byref(v1), None, C.byref(vdz), A.ptr(dwp), None, C.byref(d), st):
                 return
             A.call("segsde_conv2d_wgrad", C.byref(v1), None, C.byref(vdz), A.ptr(dwp), None, C.byref(d), st)
-        ops._timed("wgrad", 2.0 * n * ho * wo * cout * k, launch_w, desc)
-        dw = torch.empty_like(w)
+        ops._timed("wgrad", flops, launch_w, desc)
         A.call("segsde_copy_rows", A.ptr(dwp), C.c_int(kpad), A.ptr(dw), C.c_int(k), C.c_int(cout), C.c_int(k), st)
         return None, None, dw, None, None, None
 

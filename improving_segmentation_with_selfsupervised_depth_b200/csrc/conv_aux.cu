@@ -221,3 +221,64 @@ extern "C" int segsde_copy_rows(const float* src, int ld_src, float* dst, int ld
   copy_rows_kernel<<<cdiv((long long)rows * ld_dst, 256), 256, 0, as_stream(stream)>>>(src, ld_src, dst, ld_dst, rows, ncopy);
   return launched();
 }
+
+// ------------------------------------------------------------------------------------------------
+// Stem without im2col: zero-haloed, channel-padded NHWC copy of the normalised frames (read by the tensor-core
+// kernels through an overlapping row-band view) and the matching weight repack.
+// ------------------------------------------------------------------------------------------------
+namespace segsde {
+// one thread per padded pixel: reads c1 + c2 planar values (coalesced along x), writes P contiguous floats
+template <int P>
+__global__ void __launch_bounds__(256) stem_pack_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int c1,
+                                                        int c2, int n, int h, int w, int halo, int wp,
+                                                        float* __restrict__ xp) {
+  const int hp = h + 2 * halo;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n * hp * wp) return;
+  const int px = (int)(i % wp); const long long q = i / wp;
+  const int py = (int)(q % hp); const int b = (int)(q / hp);
+  const int x = px - halo, y = py - halo;
+  float v[P];
+#pragma unroll
+  for (int c = 0; c < P; ++c) v[c] = 0.f;
+  if (x >= 0 && x < w && y >= 0 && y < h) {
+    const long long plane = (long long)h * w, o = (long long)y * w + x;
+#pragma unroll
+    for (int c = 0; c < P; ++c) {
+      if (c < c1) v[c] = (__ldg(x1 + ((long long)b * c1 + c) * plane + o) - 0.45f) / 0.225f;
+      else if (c < c1 + c2) v[c] = (__ldg(x2 + ((long long)b * c2 + (c - c1)) * plane + o) - 0.45f) / 0.225f;
+    }
+  }
+  float4* dst = reinterpret_cast<float4*>(xp + i * P);
+#pragma unroll
+  for (int j = 0; j < P / 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+__global__ void stem_pack_w_kernel(float* __restrict__ w, float* __restrict__ wp, int cout, int kh, int kw, int cin, int P,
+                                   int dir) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = 8 * P;
+  if (i >= cout * kh * row) return;
+  const int j = i % row, ky = (i / row) % kh, co = i / (row * kh);
+  const int kx = j / P, c = j % P;
+  const bool real = kx < kw && c < cin;
+  const long long wi = (((long long)co * kh + ky) * kw + kx) * cin + c;
+  if (dir == 0) wp[i] = real ? w[wi] : 0.f;
+  else if (real) w[wi] = wp[i];
+}
+}  // namespace segsde
+
+extern "C" int segsde_stem_pack(const float* x1, const float* x2, int c1, int c2, int n, int h, int w, int halo, int wp,
+                                int P, float* xp, void* stream) {
+  if (!x1 || !xp || c1 < 1 || c2 < 0 || (c2 > 0 && !x2) || n < 1 || h < 1 || w < 1 || halo < 0) return SEGSDE_E_ARG;
+  if ((P != 4 && P != 8) || c1 + c2 > P || wp < w + 2 * halo) return SEGSDE_E_ARG;
+  if (reinterpret_cast<uintptr_t>(xp) & 15) return SEGSDE_E_ARG;
+  const long long total = (long long)n * (h + 2 * halo) * wp;
+  if (P == 4) stem_pack_kernel<4><<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(x1, x2, c1, c2, n, h, w, halo, wp, xp);
+  else stem_pack_kernel<8><<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(x1, x2, c1, c2, n, h, w, halo, wp, xp);
+  return launched();
+}
+extern "C" int segsde_stem_pack_w(float* w, float* wp, int cout, int kh, int kw, int cin, int P, int dir, void* stream) {
+  if (!w || !wp || cout < 1 || kh < 1 || kw < 1 || kw > 8 || cin < 1 || cin > P || (dir != 0 && dir != 1)) return SEGSDE_E_ARG;
+  stem_pack_w_kernel<<<cdiv((long long)cout * kh * 8 * P, 256), 256, 0, as_stream(stream)>>>(w, wp, cout, kh, kw, cin, P, dir);
+  return launched();
+}

@@ -308,6 +308,7 @@ static int fill(ConvP& p, const segsde_nhwc_t* x1, const segsde_nhwc_t* x2, cons
   p.x1 = mk(x1); p.x2 = mk(x2); p.y = mk(y);
   p.C1 = x1 ? x1->c : 0; p.C2 = x2 ? x2->c : 0; p.Ctot = p.C1 + p.C2; p.Cout = y->c;
   if (p.Ctot < 1 || d->kh < 1 || d->kw < 1 || d->stride < 1 || d->dil < 1 || d->pad < 0) return SEGSDE_E_ARG;
+  if (d->stride_w && d->stride_w != d->stride) return SEGSDE_E_UNSUPPORTED;   // anisotropic stride: tensor-core route only
   const segsde_nhwc_t* ref = x1 ? x1 : x2;
   const int up = (x1 && d->up1) ? 2 : 1;
   p.Hc = x1 ? x1->h * up : x2->h; p.Wc = x1 ? x1->w * up : x2->w;

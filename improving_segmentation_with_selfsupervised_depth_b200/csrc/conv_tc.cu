@@ -243,6 +243,7 @@ struct TcConvP {
   int C[2];                   // channels of the two sources (multiples of 32; C[1] may be 0)
   int Ctot, Cout;
   int kh, kw, stride, pad, dil;
+  int stride_w;               // horizontal stride (= stride except for the stem's row-band view)
   int Ho, Wo, N;
   int BW, BH, tiles_w, tiles_h, tiles_n;   // pixel tile = BW x BH (=128), tiles_n = Cout / BN
   long long total_tiles;
@@ -298,7 +299,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int w0 = tw * p.BW, h0 = th * p.BH;
         for (int tap = 0; tap < p.kh * p.kw; ++tap) {
           const int r = tap / p.kw, s = tap % p.kw;
-          const int wi = w0 * p.stride - p.pad + s * p.dil, hi = h0 * p.stride - p.pad + r * p.dil;
+          const int wi = w0 * p.stride_w - p.pad + s * p.dil, hi = h0 * p.stride - p.pad + r * p.dil;
           for (int kc = 0; kc < kchunks; ++kc) {
             mbar_wait(empty0 + 8 * stage, phase ^ 1);
             const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES), sb = sa + A_BYTES;
@@ -547,6 +548,7 @@ struct TcWgradP {
   float* dw;                  // [Cout][Ktot]
   int C[2], Ctot, Cout, Ktot;
   int kh, kw, pad, dil;
+  int stride_h;               // vertical stride (the horizontal one is 1)
   int Ho, Wo, N;
   int wchunks;                // Wo / 32
   long long chunks;           // N * Ho * wchunks
@@ -617,7 +619,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant_
         const uint32_t fb = full0 + 8 * stage;
         mbar_expect_tx(fb, (ngroups + BN / 32) * 4096);
         for (int g = 0; g < ngroups; ++g)
-          tma_load_4d(sa + g * 4096, g_src[g] ? &tmX1 : &tmX0, fb, g_c[g], w0 + g_dw[g], h + g_dh[g], n);
+          tma_load_4d(sa + g * 4096, g_src[g] ? &tmX1 : &tmX0, fb, g_c[g], w0 + g_dw[g], h * p.stride_h + g_dh[g], n);
 #pragma unroll
         for (int j = 0; j < BN / 32; ++j) tma_load_4d(sb + j * 4096, &tmDy, fb, nt * BN + j * 32, w0, h, n);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -821,12 +823,13 @@ static bool tc_init() {
 
 // NHWC activation view -> 4-D map (C, W, H, N), box (32, bw, bh, 1), optional element stride on W/H
 static bool make_act_map(CUtensorMap* m, const View& v, int bw, int bh, int estride,
-                         CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+                         CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, int estride_w = 0) {
+  if (!estride_w) estride_w = estride;
   if ((reinterpret_cast<uintptr_t>(v.p) & 15) || (v.sw % 4) || (v.sh % 4) || (v.sn % 4) || (v.c % 4)) return false;
   cuuint64_t dims[4] = {(cuuint64_t)v.c, (cuuint64_t)v.w, (cuuint64_t)v.h, (cuuint64_t)v.n};
   cuuint64_t strides[3] = {(cuuint64_t)v.sw * 4, (cuuint64_t)v.sh * 4, (cuuint64_t)v.sn * 4};
-  cuuint32_t box[4] = {32, (cuuint32_t)(bw * estride), (cuuint32_t)(bh * estride), 1};
-  cuuint32_t es[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
+  cuuint32_t box[4] = {32, (cuuint32_t)(bw * estride_w), (cuuint32_t)(bh * estride), 1};
+  cuuint32_t es[4] = {1, (cuuint32_t)estride_w, (cuuint32_t)estride, 1};
   if (box[1] > 256 || box[2] > 256) return false;
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, v.p, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -952,15 +955,17 @@ extern "C" int segsde_conv2d_fwd_tc_stats(const segsde_nhwc_t* x1, const segsde_
   const int C1 = v1.c, C2 = v2.p ? v2.c : 0, Cout = vy.c;
   if (C1 % 32 || C2 % 32 || Cout % 32) return SEGSDE_E_UNSUPPORTED;
   if (v2.p && (v2.h != v1.h || v2.w != v1.w || v2.n != v1.n)) return SEGSDE_E_ARG;
+  const int stride_w = d->stride_w ? d->stride_w : d->stride;
+  if (stride_w != 1 && stride_w != 2) return SEGSDE_E_UNSUPPORTED;
   const int Ho = (v1.h + 2 * d->pad - d->dil * (d->kh - 1) - 1) / d->stride + 1;
-  const int Wo = (v1.w + 2 * d->pad - d->dil * (d->kw - 1) - 1) / d->stride + 1;
+  const int Wo = (v1.w + 2 * d->pad - d->dil * (d->kw - 1) - 1) / stride_w + 1;
   if (vy.h != Ho || vy.w != Wo || vy.n != v1.n) return SEGSDE_E_ARG;
   if (!vec4_ok(vy)) return SEGSDE_E_UNSUPPORTED;
   const int BN = (Cout % 128 == 0) ? 128 : (Cout % 64 == 0 ? 64 : 32);
   TcConvP p;
   p.y = vy; p.bias = bias; p.act = d->act; p.stats = stats;
   p.C[0] = C1; p.C[1] = C2; p.Ctot = C1 + C2; p.Cout = Cout;
-  p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pad = d->pad; p.dil = d->dil;
+  p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pad = d->pad; p.dil = d->dil; p.stride_w = stride_w;
   p.Ho = Ho; p.Wo = Wo; p.N = v1.n;
   p.BW = Wo >= 128 ? 128 : pow2_floor(Wo < 1 ? 1 : Wo);
   if (p.BW < 8) return SEGSDE_E_UNSUPPORTED;
@@ -985,8 +990,8 @@ extern "C" int segsde_conv2d_fwd_tc_stats(const segsde_nhwc_t* x1, const segsde_
                        : launch_conv3x3<64, 3>(a0, a1, b, r, as_stream(stream));
     }
   }
-  if (!make_act_map(&a0, v1, p.BW, p.BH, d->stride)) return SEGSDE_E_UNSUPPORTED;
-  if (C2) { if (!make_act_map(&a1, v2, p.BW, p.BH, d->stride)) return SEGSDE_E_UNSUPPORTED; } else a1 = a0;
+  if (!make_act_map(&a0, v1, p.BW, p.BH, d->stride, CU_TENSOR_MAP_SWIZZLE_128B, stride_w)) return SEGSDE_E_UNSUPPORTED;
+  if (C2) { if (!make_act_map(&a1, v2, p.BW, p.BH, d->stride, CU_TENSOR_MAP_SWIZZLE_128B, stride_w)) return SEGSDE_E_UNSUPPORTED; } else a1 = a0;
   if (!make_w_map(&b, w, d->kh * d->kw * p.Ctot, Cout, BN)) return SEGSDE_E_UNSUPPORTED;
   if (BN == 128) return launch_conv<128>(a0, a1, b, p, as_stream(stream));
   if (BN == 64) return launch_conv<64>(a0, a1, b, p, as_stream(stream));
@@ -1006,15 +1011,18 @@ extern "C" int segsde_conv2d_wgrad_tc(const segsde_nhwc_t* x1, const segsde_nhwc
   if (!x1 || !x1->ptr || !dy || !dy->ptr || !dw || !d) return SEGSDE_E_ARG;
   if (!tc_init()) return SEGSDE_E_UNSUPPORTED;
   if (dbias) return SEGSDE_E_UNSUPPORTED;      // bias gradient is produced by segsde_act_bwd_bias
-  if (d->pad_mode != SEGSDE_PAD_ZERO || d->up1 || d->nchw_norm_in || d->stride != 1) return SEGSDE_E_UNSUPPORTED;
+  if (d->pad_mode != SEGSDE_PAD_ZERO || d->up1 || d->nchw_norm_in) return SEGSDE_E_UNSUPPORTED;
+  // strided layers arrive here as stride 1 on a zero-stuffed dy; the one exception is a vertical stride with
+  // horizontal stride 1 (the stem's row-band view), which the generic kernel handles in its TMA coordinates
+  if (d->stride != 1 && !(d->stride_w == 1 && d->stride == 2)) return SEGSDE_E_UNSUPPORTED;
   View v1 = mk(x1), v2 = mk(x2), vd = mk(dy);
   const int C1 = v1.c, C2 = v2.p ? v2.c : 0, Cout = vd.c;
   if (C1 % 32 || C2 % 32 || Cout % 32) return SEGSDE_E_UNSUPPORTED;
-  const int Ho = v1.h + 2 * d->pad - d->dil * (d->kh - 1), Wo = v1.w + 2 * d->pad - d->dil * (d->kw - 1);
+  const int Ho = (v1.h + 2 * d->pad - d->dil * (d->kh - 1) - 1) / d->stride + 1, Wo = v1.w + 2 * d->pad - d->dil * (d->kw - 1);
   if (vd.h != Ho || vd.w != Wo || vd.n != v1.n) return SEGSDE_E_ARG;
   if (Wo % 32) return SEGSDE_E_UNSUPPORTED;
   const int BN = (Cout % 128 == 0) ? 128 : (Cout % 64 == 0 ? 64 : 32);
-  if (wg3_mode() && d->kh == 3 && d->kw == 3 && BN >= 64 && 32 + 2 * d->dil <= 256) {
+  if (wg3_mode() && d->kh == 3 && d->kw == 3 && d->stride == 1 && BN >= 64 && 32 + 2 * d->dil <= 256) {
     TcWg3P q;
     q.dw = dw; q.C[0] = C1; q.C[1] = C2; q.Ctot = C1 + C2; q.Cout = Cout; q.Ktot = 9 * q.Ctot;
     q.pad = d->pad; q.dil = d->dil; q.Ho = Ho; q.Wo = Wo; q.N = v1.n; q.wchunks = Wo / 32;
@@ -1040,7 +1048,7 @@ extern "C" int segsde_conv2d_wgrad_tc(const segsde_nhwc_t* x1, const segsde_nhwc
   }
   TcWgradP p;
   p.dw = dw; p.C[0] = C1; p.C[1] = C2; p.Ctot = C1 + C2; p.Cout = Cout; p.Ktot = d->kh * d->kw * p.Ctot;
-  p.kh = d->kh; p.kw = d->kw; p.pad = d->pad; p.dil = d->dil;
+  p.kh = d->kh; p.kw = d->kw; p.pad = d->pad; p.dil = d->dil; p.stride_h = d->stride;
   p.Ho = Ho; p.Wo = Wo; p.N = v1.n; p.wchunks = Wo / 32;
   p.chunks = (long long)p.N * Ho * p.wchunks;
   p.mtiles = cdiv(p.Ktot, 128); p.ntiles = Cout / BN;

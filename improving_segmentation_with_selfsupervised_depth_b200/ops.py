@@ -93,10 +93,10 @@ def ohwi(w):
 # -------------------------------------------------------------------------------------------------
 # convolution
 # -------------------------------------------------------------------------------------------------
-def _desc(kh, kw, stride, pad, dil, pad_mode, up1, act, nchw):
+def _desc(kh, kw, stride, pad, dil, pad_mode, up1, act, nchw, stride_w=0):
     d = A.ConvDesc()
     d.kh, d.kw, d.stride, d.pad, d.dil = kh, kw, stride, pad, dil
-    d.pad_mode, d.up1, d.act, d.nchw_norm_in = pad_mode, int(up1), act, int(nchw)
+    d.pad_mode, d.up1, d.act, d.nchw_norm_in, d.stride_w = pad_mode, int(up1), act, int(nchw), stride_w
     return d
 
 

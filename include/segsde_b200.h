@@ -62,6 +62,8 @@ typedef struct {
   int32_t act;          /* SEGSDE_ACT_* fused after bias */
   int32_t nchw_norm_in; /* 1: x1.ptr is an NCHW planar image and (x-0.45)/0.225 is applied on load
                            (resnet_encoder.py:92); x1 strides are then ignored */
+  int32_t stride_w;     /* 0 = same as `stride`; otherwise the horizontal stride while `stride` is the vertical one
+                           (tensor-core fwd / wgrad only — the stem's row-band view, segsde_stem_pack) */
 } segsde_conv_desc_t;
 
 /* y = act(conv(cat(x1[up], x2), w) + bias).  x2 may be NULL (c=0).  bias may be NULL.
@@ -113,6 +115,18 @@ int segsde_act_bwd_bias(const segsde_nhwc_t* y, const segsde_nhwc_t* dy, const s
 int segsde_stem_im2col(const float* x1, const float* x2, int c1, int c2, int n, int h, int w, int kh, int kw,
                        int stride, int pad, int kpad, float* cols, void* stream);
 int segsde_copy_rows(const float* src, int ld_src, float* dst, int ld_dst, int rows, int ncopy, void* stream);
+/* Stem without im2col (resnet_encoder.py:92-93, 7x7 / stride 2 / pad 3 on 3- or 6-channel frames).
+ * stem_pack: xp[n][h+2*halo][wp][P] = (x-0.45)/0.225 of the NCHW frames x1 (c1 ch) ++ x2 (c2 ch, may be NULL) at
+ * [.., y+halo, x+halo, c], zero in the halo, for x >= w+halo and for c >= c1+c2 (P = 4 or 8 channels per pixel).
+ * An output pixel (oy, ox) then reads, for each kernel row ky, the 8*P contiguous floats that start at padded
+ * pixel (2*oy+ky, 2*ox): the convolution is a (kh x 1)-tap implicit GEMM over the OVERLAPPING view
+ * {c = 8*P, w = W/2 with stride 2*P floats, h = H+2*halo} with vertical stride 2 (segsde_conv_desc_t.stride_w = 1),
+ * K = kh*8*P — the activation is read once instead of being expanded 12x by im2col.
+ * stem_pack_w: dir 0: wp[co][ky][kx*P+c] = w[co][ky][kx][c] (zero for kx = 7 or c >= cin); dir 1: the inverse
+ * gather (w <- wp) used on the weight gradient.  w: [cout][kh][kw][cin] (OHWI), kw <= 8. */
+int segsde_stem_pack(const float* x1, const float* x2, int c1, int c2, int n, int h, int w, int halo, int wp, int P,
+                     float* xp, void* stream);
+int segsde_stem_pack_w(float* w, float* wp, int cout, int kh, int kw, int cin, int P, int dir, void* stream);
 /* Disparity heads (C -> 1, 3x3, pad 1) on the tensor cores: y = act(bias + sum_t z[resolve(p + tap_t)][t]) over the
  * 9 tap planes z = 1x1conv(x) (first 9 of >= 9 channels), and the adjoint stencil gcol[q][t] (32 channels, 9 used)
  * of dy that turns dgrad / wgrad into 1x1 GEMMs. */

@@ -153,3 +153,43 @@ def test_tc_disparity_head(cin, H, W, reflect):
     assert rel_err(gx.grad, x.grad) < TOL
     assert rel_err(gw.grad, w.grad) < TOL
     assert rel_err(gb.grad, b.grad) < TOL
+
+
+@pytest.mark.parametrize("route", ["band", "im2col"])
+@pytest.mark.parametrize("c2,H,W", [(0, 32, 64), (3, 20, 128), (0, 64, 256)])
+def test_tc_stem(route, c2, H, W, monkeypatch):
+    """7x7 / s2 / pad 3 stem on NCHW frames with the (x-0.45)/0.225 normalisation (resnet_encoder.py:92-93): the
+    row-band route (overlapping TMA view of the packed frames, no im2col) and the im2col fallback, forward, fused
+    BatchNorm statistics and weight gradient against PyTorch fp32."""
+    A, ops = _mods()
+    monkeypatch.setenv("SEGSDE_STEM_BAND", "1" if route == "band" else "0")
+    ops.USE_TC = True
+    try:
+        g = torch.Generator().manual_seed(11 + c2 + H)
+        n = 2
+        x1 = torch.rand(n, 3, H, W, generator=g)
+        x2 = torch.rand(n, c2, H, W, generator=g) if c2 else None
+        w = torch.randn(64, 3 + c2, 7, 7, generator=g) * 0.05
+        xin = torch.cat([x1, x2], 1) if c2 else x1
+        wr = w.clone().requires_grad_()
+        ref = F.conv2d((xin - 0.45) / 0.225, wr, None, 2, 3)
+        gy = torch.randn(ref.shape, generator=g)
+        ref.backward(gy)
+        wt = w.cuda().contiguous(memory_format=torch.channels_last).requires_grad_()
+        sums = torch.zeros(3 * 64, device="cuda", dtype=torch.float64)
+        ops.PROFILE, ops.PROFILE_DESC = [], []
+        y = ops.conv2d(x1.cuda(), wt, None, x2=x2.cuda() if c2 else None, stride=2, pad=3, nchw_norm_in=True, bn_stats=sums)
+        y.backward(gy.cuda())
+        assert any(route in d for d in ops.PROFILE_DESC), ops.PROFILE_DESC
+        assert rel_err(y, ref) < TOL
+        assert rel_err(wt.grad, wr.grad) < TOL
+        cnt = ref.numel() / 64
+        mean = ref.detach().double().mean((0, 2, 3))
+        # sums = (sum(y - shift), sum((y - shift)^2), shift) per channel
+        s = sums.cpu().view(3, 64)
+        assert rel_err(s[0] / cnt + s[2], mean) < TOL
+        var = ref.detach().double().var((0, 2, 3), unbiased=False)
+        assert rel_err(s[1] / cnt - (s[0] / cnt) ** 2, var) < 2 * TOL
+    finally:
+        ops.PROFILE, ops.PROFILE_DESC = None, None
+        ops.USE_TC = False
