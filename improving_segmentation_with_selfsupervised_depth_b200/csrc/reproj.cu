@@ -139,8 +139,8 @@ __global__ void __launch_bounds__(NTHREADS, GRAD ? 3 : 4) reproj_kernel(ReprojK 
   float* s_src = s_tgt + 3 * NP;             // [2][3][NP]
   float* s_pred = s_src + 6 * NP;            // [2][3][NP]
   float* s_wgt = s_pred + 6 * NP;            // [2][NC]   (GRAD) selection weight per frame
-  float* s_coef = s_wgt + 2 * NC;            // [3][NC]   (GRAD)
-  float* s_red = s_coef + 3 * NC;            // [8][25]
+  float* s_coef = s_wgt + 2 * NC;            // [2][3][3][NC] (GRAD) affine SSIM-gradient coefficients per (frame, channel)
+  float* s_red = s_coef + (GRAD ? 18 : 0) * NC;   // [8][25]
   __shared__ float sP[2][12];
   __shared__ float sIK[9];
 
@@ -264,6 +264,7 @@ __global__ void __launch_bounds__(NTHREADS, GRAD ? 3 : 4) reproj_kernel(ReprojK 
       for (int dx = -1; dx <= 1; ++dx)
         wo[(dy + 1) * 3 + dx + 1] = (reflect_idx(cy + dy, H) - ry0) * RW + (reflect_idx(cx + dx, W) - rx0);
     const int ctr = wo[4];
+    const int ci = (cy - (y0 - RC)) * CW + (cx - (x0 - RC));     // this centre's slot in the [NC] arrays
     float cand[4] = {0.f, 0.f, 0.f, 0.f};   // [identity f0, identity f1, reproj f0, reproj f1]
     // images: m = 0,1 reprojected frames; m = 2,3 raw source frames (identity candidates).  The identity
     // candidates do not depend on the scale: scale 0 stores them (ident_mode 1), coarser scales read them back
@@ -285,8 +286,26 @@ __global__ void __launch_bounds__(NTHREADS, GRAD ? 3 : 4) reproj_kernel(ReprojK 
           float sx = 0.f, sxx = 0.f, sxy = 0.f;
 #pragma unroll
           for (int t = 0; t < 9; ++t) { const float xv = X[wo[t]]; sx += xv; sxx = fmaf(xv, xv, sxx); sxy = fmaf(xv, yw[t], sxy); }
-          const float v = ssim_from_sums(sx, sy, sxx, syy, sxy, nullptr);
+          Stats st;
+          const float v = ssim_from_sums(sx, sy, sxx, syy, sxy, (GRAD && m < 2) ? &st : nullptr);
           ssim_acc[m] += fminf(fmaxf(v, 0.f), 1.f);
+          if (GRAD && m < 2) {
+            // d(0.85/3 * clamp(ssim)) / d x_i = A + B x_i + C y_i for every x_i of this window (the window
+            // statistics are already here; stage 4 only gathers).  Zero where the clamp is active.
+            float A = 0.f, Bc = 0.f, Cc = 0.f;
+            if (v >= 0.f && v <= 1.f) {
+              const float n1 = 2.f * st.mu_x * st.mu_y + 1e-4f, n2 = 2.f * st.sxy + 9e-4f;
+              const float d1 = st.mu_x * st.mu_x + st.mu_y * st.mu_y + 1e-4f, d2 = st.sxx + st.syy + 9e-4f;
+              const float Nn = n1 * n2;
+              const float iD = 1.f / (d1 * d2);
+              const float sc = (0.85f / 3.f) * (1.f / 9.f);
+              A = -sc * (st.mu_y * (n2 - n1) * iD - Nn * st.mu_x * (d2 - d1) * iD * iD);
+              Bc = sc * Nn * d1 * iD * iD;
+              Cc = -sc * n1 * iD;
+            }
+            float* cf = s_coef + (size_t)(f * 3 + c) * 3 * NC + ci;
+            cf[0] = A; cf[NC] = Bc; cf[2 * NC] = Cc;
+          }
         }
       }
     }
@@ -335,7 +354,6 @@ __global__ void __launch_bounds__(NTHREADS, GRAD ? 3 : 4) reproj_kernel(ReprojK 
       if (k.ident_sel) k.ident_sel[(size_t)b * plane + (size_t)cy * W + cx] = reproj_won ? 1.f : 0.f;
     }
     if (GRAD) {
-      const int ci = (cy - (y0 - RC)) * CW + (cx - (x0 - RC));
       float w0 = 0.f, w1 = 0.f;
       if (reproj_won) {
         if (avg) { w0 = w1 = (F == 2 ? 0.5f : 1.f); }
@@ -358,86 +376,57 @@ __global__ void __launch_bounds__(NTHREADS, GRAD ? 3 : 4) reproj_kernel(ReprojK 
   }
   if (!GRAD) return;
 
-  // ---- stage 4 (GRAD): d mean-loss / d pred via per-centre affine coefficients --------------------
-  // ring centres outside the image never wrote s_wgt: they are never read either (gather is bounded)
+  // ---- stage 4 (GRAD): d mean-loss / d pred: gather the affine coefficients of the 3x3 centres around q -----
+  // ring centres outside the image never wrote s_wgt / s_coef: they are never read either (their slot is replaced
+  // by the thread's own with multiplicity 0)
   __syncthreads();
   float gpred[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
-  const float wssim = no_ssim ? 0.f : 0.85f / 3.f;
   const float wl1 = no_ssim ? 1.f / 3.f : 0.15f / 3.f;
+  if (own_valid) {
+    const int si = (qy - ry0) * RW + (qx - rx0);
+    const int cself = (qy - (y0 - RC)) * CW + (qx - (x0 - RC));
+    int cidx[9]; float mult[9];
 #pragma unroll
-  for (int f = 0; f < 2; ++f) {
-    if (f >= F) break;
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int py = qy + dy;
+      // multiplicity of q in centre p's reflected window (adjoint of ReflectionPad2d(1))
+      const float my = (py < 0 || py >= H) ? 0.f
+                       : 1.f + ((py == 0 && qy == 1) ? 1.f : 0.f) + ((py == H - 1 && qy == H - 2) ? 1.f : 0.f);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      if (!no_ssim) {
-        const float* X = s_pred + (f * 3 + c) * NP;
-        const float* Y = s_tgt + c * NP;
-        for (int j = tid; j < NC; j += NTHREADS) {
-          const int lx = j % CW, ly = j / CW;
-          const int cx = x0 - RC + lx, cy = y0 - RC + ly;
-          float A = 0.f, Bc = 0.f, Cc = 0.f;
-          if (cx >= 0 && cx < W && cy >= 0 && cy < H) {
-            const float wsel = s_wgt[f * NC + j];
-            if (wsel != 0.f) {
-              float sx = 0.f, sy = 0.f, sxx = 0.f, syy = 0.f, sxy = 0.f;
-#pragma unroll
-              for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-                for (int dx = -1; dx <= 1; ++dx) {
-                  const int o = (reflect_idx(cy + dy, H) - ry0) * RW + (reflect_idx(cx + dx, W) - rx0);
-                  const float xv = X[o], yv = Y[o];
-                  sx += xv; sy += yv; sxx += xv * xv; syy += yv * yv; sxy += xv * yv;
-                }
-              Stats st;
-              const float v = ssim_from_sums(sx, sy, sxx, syy, sxy, &st);
-              if (v >= 0.f && v <= 1.f) {
-                const float n1 = 2.f * st.mu_x * st.mu_y + 1e-4f, n2 = 2.f * st.sxy + 9e-4f;
-                const float d1 = st.mu_x * st.mu_x + st.mu_y * st.mu_y + 1e-4f, d2 = st.sxx + st.syy + 9e-4f;
-                const float D = d1 * d2, Nn = n1 * n2;
-                const float iD = 1.f / D;
-                const float s = wsel * wssim * (1.f / 9.f);
-                // dv/dx_i = A + B x_i + C y_i
-                A = -s * (st.mu_y * (n2 - n1) * iD - Nn * st.mu_x * (d2 - d1) * iD * iD);
-                Bc = s * Nn * d1 * iD * iD;
-                Cc = -s * n1 * iD;
-              }
-            }
-          }
-          s_coef[j] = A; s_coef[NC + j] = Bc; s_coef[2 * NC + j] = Cc;
-        }
-        __syncthreads();
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int px = qx + dx;
+        const float mx = (px < 0 || px >= W) ? 0.f
+                         : 1.f + ((px == 0 && qx == 1) ? 1.f : 0.f) + ((px == W - 1 && qx == W - 2) ? 1.f : 0.f);
+        const float m = mx * my;
+        mult[(dy + 1) * 3 + dx + 1] = m;
+        cidx[(dy + 1) * 3 + dx + 1] = m != 0.f ? cself + dy * CW + dx : cself;
       }
-      if (own_valid) {
-        const int si = (qy - ry0) * RW + (qx - rx0);
+    }
+#pragma unroll
+    for (int f = 0; f < 2; ++f) {
+      if (f >= F) break;
+      float mw[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) mw[t] = mult[t] * s_wgt[f * NC + cidx[t]];
+      const float wself = s_wgt[f * NC + cself];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
         const float xq = s_pred[(f * 3 + c) * NP + si], yq = s_tgt[c * NP + si];
         float g = 0.f;
         if (!no_ssim) {
+          const float* cf = s_coef + (size_t)(f * 3 + c) * 3 * NC;
           float sa = 0.f, sb = 0.f, sc = 0.f;
 #pragma unroll
-          for (int dy = -1; dy <= 1; ++dy) {
-            const int py = qy + dy;
-            if (py < 0 || py >= H) continue;
-            // multiplicity of q in centre p's reflected window (adjoint of ReflectionPad2d(1))
-            const float my = 1.f + ((py == 0 && qy == 1) ? 1.f : 0.f) + ((py == H - 1 && qy == H - 2) ? 1.f : 0.f);
-#pragma unroll
-            for (int dx = -1; dx <= 1; ++dx) {
-              const int px = qx + dx;
-              if (px < 0 || px >= W) continue;
-              const float mx = 1.f + ((px == 0 && qx == 1) ? 1.f : 0.f) + ((px == W - 1 && qx == W - 2) ? 1.f : 0.f);
-              const int ci = (py - (y0 - RC)) * CW + (px - (x0 - RC));
-              const float m = mx * my;
-              sa += m * s_coef[ci]; sb += m * s_coef[NC + ci]; sc += m * s_coef[2 * NC + ci];
-            }
+          for (int t = 0; t < 9; ++t) {
+            sa = fmaf(mw[t], cf[cidx[t]], sa); sb = fmaf(mw[t], cf[NC + cidx[t]], sb); sc = fmaf(mw[t], cf[2 * NC + cidx[t]], sc);
           }
           g = sa + sb * xq + sc * yq;
         }
-        const int cself = (qy - (y0 - RC)) * CW + (qx - (x0 - RC));
         const float diff = xq - yq;
         const float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
-        g += s_wgt[f * NC + cself] * wl1 * sgn;
+        g += wself * wl1 * sgn;
         gpred[f][c] = g * k.inv_count;
       }
-      if (!no_ssim) __syncthreads();
     }
   }
 
@@ -506,7 +495,7 @@ template <bool GRAD>
 static size_t reproj_smem_bytes() {
   constexpr int R = GRAD ? 2 : 1, RC = R - 1;
   constexpr int NP = (TX + 2 * R) * (TY + 2 * R), NC = (TX + 2 * RC) * (TY + 2 * RC);
-  return sizeof(float) * (size_t)(15 * NP + 5 * NC + 8 * 25);
+  return sizeof(float) * (size_t)(15 * NP + (GRAD ? 20 : 2) * NC + 8 * 25);
 }
 
 // loss = sum(partials) / count ; gT[f][b] = K[:3,:]^T (4x3) * gP (3x4)
