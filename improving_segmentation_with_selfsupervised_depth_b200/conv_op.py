@@ -123,10 +123,12 @@ class _Conv2dFn(torch.autograd.Function):
         c1 = x1e.shape[1]
         c2 = x2e.shape[1] if x2e is not None else 0
         flops_scale = 1.0
+        dz_s, d_s = None, None      # the strided dz / descriptor: wgrad takes them directly (no zero-stuffing)
         if stride == 2 and tc_ch and mode_e == A.PAD_ZERO and not up_e and not nchw and (need1 or need2 or needw):
             # zero-stuff dz onto the stride-1 output grid: dgrad and wgrad become stride-1 problems
             hs = x1e.shape[2] + 2 * pad_e - dil * (kh - 1)
             ws = x1e.shape[3] + 2 * pad_e - dil * (kw - 1)
+            dz_s, d_s = dz, ops._desc(kh, kw, 2, pad_e, dil, mode_e, up_e, A.ACT_NONE, nchw)
             dzu = ops.cl_empty(n, cout, hs, ws, dev, zero=True)
             A.call("segsde_copy_nhwc", C.byref(ops.view(dz)), C.byref(ops.view(dzu[:, :, ::2, ::2][:, :, :ho, :wo])), st)
             dz, stride, flops_scale = dzu, 1, 0.25        # algorithmic flops stay those of the strided conv
@@ -198,6 +200,9 @@ class _Conv2dFn(torch.autograd.Function):
             vdz = ops.view(dz)
 
             def launch_w():
+                if dz_s is not None and A.try_call("segsde_conv2d_wgrad_tc", C.byref(v1), ops._ref(v2),
+                                                   C.byref(ops.view(dz_s)), A.ptr(dw), None, C.byref(d_s), st):
+                    return
                 if _tc_enabled() and not nchw and A.try_call("segsde_conv2d_wgrad_tc", C.byref(v1), ops._ref(v2),
                                                              C.byref(vdz), A.ptr(dw), None, C.byref(d), st):
                     return

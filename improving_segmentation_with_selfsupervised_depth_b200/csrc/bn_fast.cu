@@ -124,6 +124,53 @@ __global__ void __launch_bounds__(256) bn_apply_fast_kernel(Rows x, Rows res, Ro
   }
 }
 
+// Train-mode forward: bn_finalize folded into the apply pass.  Every CTA turns the fp64 sums into per-channel
+// mean, scale = invstd * gamma and beta in shared memory (C <= 2048), CTA 0 also publishes mean / invstd for the
+// backward pass and updates the running statistics.
+__global__ void __launch_bounds__(256) bn_apply_train_fast_kernel(Rows x, Rows res, Rows y, long long total4, int cq,
+                                                                  int cq_shift, const double* __restrict__ sums, int C,
+                                                                  double count, float eps, float momentum,
+                                                                  const float* __restrict__ gamma,
+                                                                  const float* __restrict__ beta, int act,
+                                                                  float* __restrict__ mean_o, float* __restrict__ invstd_o,
+                                                                  float* __restrict__ rmean, float* __restrict__ rvar) {
+  extern __shared__ __align__(16) float s_ss[];       // [C] mean, [C] scale, [C] beta
+  float* s_mean = s_ss; float* s_scale = s_ss + C; float* s_beta = s_ss + 2 * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    // sums hold sum(x - s), sum((x - s)^2) and the shift s (0 when they come from a convolution epilogue)
+    const double ms = sums[c] / count;
+    double var = sums[C + c] / count - ms * ms;
+    if (var < 0.0) var = 0.0;
+    const double m = ms + sums[2 * C + c];
+    const float mf = (float)m, is = (float)(1.0 / sqrt(var + (double)eps));
+    s_mean[c] = mf;
+    s_scale[c] = is * (gamma ? gamma[c] : 1.f);
+    s_beta[c] = beta ? beta[c] : 0.f;
+    if (blockIdx.x == 0) {
+      mean_o[c] = mf; invstd_o[c] = is;
+      if (rmean) {
+        const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+        rmean[c] = (1.f - momentum) * rmean[c] + momentum * mf;
+        rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unbiased;
+      }
+    }
+  }
+  __syncthreads();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    long long p; int c4;
+    if (cq_shift >= 0) { p = i >> cq_shift; c4 = (int)(i & (cq - 1)); } else { p = i / cq; c4 = (int)(i - p * cq); }
+    const int c = c4 * 4;
+    const float4 v = ld4(x.p + p * x.ld + c);
+    const float4 m = ld4(s_mean + c), sc = ld4(s_scale + c), b = ld4(s_beta + c);
+    float4 o;
+    o.x = (v.x - m.x) * sc.x + b.x; o.y = (v.y - m.y) * sc.y + b.y;
+    o.z = (v.z - m.z) * sc.z + b.z; o.w = (v.w - m.w) * sc.w + b.w;
+    if (res.p) { const float4 r = ld4(res.p + p * res.ld + c); o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
+    if (act == SEGSDE_ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    st4(y.p + p * y.ld + c, o);
+  }
+}
+
 __global__ void __launch_bounds__(256) bn_bwd_apply_fast_kernel(Rows x, Rows y, Rows dy, Rows dx, Rows dres, long long total4,
                                                                 int cq, int cq_shift, int C,
                                                                 const float* __restrict__ mean,
@@ -211,6 +258,19 @@ int bn_apply_fast(const View& x, const View& res, const View& y, const float* me
   Rows none; none.p = nullptr; none.ld = 0;
   bn_apply_fast_kernel<<<(unsigned)blocks, 256, 0, st>>>(rows_of(x), res.p ? rows_of(res) : none, rows_of(y), total4, cq,
                                                         shift_of(cq), mean, invstd, gamma, beta, act);
+  return launched();
+}
+int bn_apply_train_fast(const View& x, const View& res, const View& y, const double* sums, long long count, float eps,
+                        float momentum, const float* gamma, const float* beta, int act, float* mean, float* invstd,
+                        float* rmean, float* rvar, cudaStream_t st) {
+  const long long P = (long long)x.n * x.h * x.w;
+  const int cq = x.c / 4;
+  const long long total4 = P * cq;
+  long long blocks = cdiv(total4, 256 * 4); if (blocks > 148 * 16) blocks = 148 * 16; if (blocks < 1) blocks = 1;
+  Rows none; none.p = nullptr; none.ld = 0;
+  bn_apply_train_fast_kernel<<<(unsigned)blocks, 256, 3 * x.c * sizeof(float), st>>>(
+      rows_of(x), res.p ? rows_of(res) : none, rows_of(y), total4, cq, shift_of(cq), sums, x.c, (double)count, eps, momentum,
+      gamma, beta, act, mean, invstd, rmean, rvar);
   return launched();
 }
 int bn_bwd_apply_fast(const View& x, const View& y, const View& dy, const View& dx, const View& dres, const float* mean,

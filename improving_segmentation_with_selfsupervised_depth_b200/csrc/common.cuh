@@ -134,6 +134,9 @@ int bn_bwd_reduce_fast(const View& x, const View& y, const View& dy, const float
 int act_bwd_bias_fast(const View& y, const View& dy, const View& dz, int act, float* dbias, cudaStream_t st);
 int bn_apply_fast(const View& x, const View& res, const View& y, const float* mean, const float* invstd, const float* gamma,
                   const float* beta, int act, cudaStream_t st);
+int bn_apply_train_fast(const View& x, const View& res, const View& y, const double* sums, long long count, float eps,
+                        float momentum, const float* gamma, const float* beta, int act, float* mean, float* invstd,
+                        float* rmean, float* rvar, cudaStream_t st);
 int bn_bwd_apply_fast(const View& x, const View& y, const View& dy, const View& dx, const View& dres, const float* mean,
                       const float* invstd, const float* gamma, int relu, int training, const double* red, long long count,
                       cudaStream_t st);

@@ -301,6 +301,25 @@ __global__ void act_fwd_kernel(View x, View y, int act) {
   y.p[y.off(n, h, w) + c] = act_apply(x.p[x.off(n, h, w) + c], act);
 }
 
+// 1x1 convolution over a handful of pixels (the ASPP image-pooling branch, model_parts.py:28-40: B x 2048 x 1 x 1):
+// one warp per (pixel, output channel) dot product — the tiled kernel would run it on two CTAs.
+__global__ void __launch_bounds__(256) conv1x1_fewpx_kernel(View x, View y, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, int C, int Cout, int act,
+                                                            long long P) {
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= P * Cout) return;
+  const int co = (int)(wid % Cout); long long q = wid / Cout;
+  const int wq = (int)(q % y.w); q /= y.w;
+  const int hq = (int)(q % y.h); const int n = (int)(q / y.h);
+  const float* xp = x.p + x.off(n, hq, wq);
+  const float* wp = w + (long long)co * C;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s = fmaf(__ldg(xp + c), __ldg(wp + c), s);
+  s = warp_sum(s);
+  if (lane == 0) y.p[y.off(n, hq, wq) + co] = act_apply(s + (bias ? bias[co] : 0.f), act);
+}
+
 static int fill(ConvP& p, const segsde_nhwc_t* x1, const segsde_nhwc_t* x2, const segsde_nhwc_t* y,
                 const segsde_conv_desc_t* d, bool x_optional) {
   if (!y || !y->ptr || !d) return SEGSDE_E_ARG;
@@ -338,6 +357,11 @@ extern "C" int segsde_conv2d_fwd(const segsde_nhwc_t* x1, const segsde_nhwc_t* x
   if (p.Cout == 1 && !p.x2.p) {
     rc = c1_fwd(p.x1, p.y, w, bias, d, as_stream(stream));
     if (rc != SEGSDE_E_UNSUPPORTED) return rc;
+  }
+  if (p.kh == 1 && p.kw == 1 && p.stride == 1 && p.pad == 0 && !p.x2.p && !p.nchw && !p.up1 && p.P <= 256) {
+    conv1x1_fewpx_kernel<<<cdiv(p.P * p.Cout * 32, 256), 256, 0, as_stream(stream)>>>(p.x1, p.y, w, bias, p.C1, p.Cout,
+                                                                                       p.act, p.P);
+    return launched();
   }
   p.w = w; p.bias = bias;
   dim3 grid(cdiv(p.P, BM), cdiv(p.Cout, BN));
@@ -384,7 +408,7 @@ extern "C" int segsde_conv2d_wgrad(const segsde_nhwc_t* x1, const segsde_nhwc_t*
   const int gx = cdiv(p.Cout, BM), gy = cdiv(p.Ktot, BN);
   long long want = (148LL * 6) / ((long long)gx * gy);
   if (want < 1) want = 1;
-  long long chunks = cdiv(p.P, 512);
+  long long chunks = cdiv(p.P, 128);
   if (chunks > want) chunks = want;
   if (chunks < 1) chunks = 1;
   if (chunks > 65535) chunks = 65535;

@@ -548,7 +548,7 @@ struct TcWgradP {
   float* dw;                  // [Cout][Ktot]
   int C[2], Ctot, Cout, Ktot;
   int kh, kw, pad, dil;
-  int stride_h;               // vertical stride (the horizontal one is 1)
+  int stride_h, stride_w;     // strides of the convolution (the x boxes use TMA element strides horizontally)
   int Ho, Wo, N;
   int wchunks;                // Wo / 32
   long long chunks;           // N * Ho * wchunks
@@ -619,7 +619,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant_
         const uint32_t fb = full0 + 8 * stage;
         mbar_expect_tx(fb, (ngroups + BN / 32) * 4096);
         for (int g = 0; g < ngroups; ++g)
-          tma_load_4d(sa + g * 4096, g_src[g] ? &tmX1 : &tmX0, fb, g_c[g], w0 + g_dw[g], h * p.stride_h + g_dh[g], n);
+          tma_load_4d(sa + g * 4096, g_src[g] ? &tmX1 : &tmX0, fb, g_c[g], w0 * p.stride_w + g_dw[g], h * p.stride_h + g_dh[g], n);
 #pragma unroll
         for (int j = 0; j < BN / 32; ++j) tma_load_4d(sb + j * 4096, &tmDy, fb, nt * BN + j * 32, w0, h, n);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -1012,17 +1012,20 @@ extern "C" int segsde_conv2d_wgrad_tc(const segsde_nhwc_t* x1, const segsde_nhwc
   if (!tc_init()) return SEGSDE_E_UNSUPPORTED;
   if (dbias) return SEGSDE_E_UNSUPPORTED;      // bias gradient is produced by segsde_act_bwd_bias
   if (d->pad_mode != SEGSDE_PAD_ZERO || d->up1 || d->nchw_norm_in) return SEGSDE_E_UNSUPPORTED;
-  // strided layers arrive here as stride 1 on a zero-stuffed dy; the one exception is a vertical stride with
-  // horizontal stride 1 (the stem's row-band view), which the generic kernel handles in its TMA coordinates
-  if (d->stride != 1 && !(d->stride_w == 1 && d->stride == 2)) return SEGSDE_E_UNSUPPORTED;
+  // stride 2 (either direction): the generic kernel strides its x boxes (TMA element strides horizontally, the
+  // row coordinate vertically); dy stays dense
+  if (d->stride != 1 && d->stride != 2) return SEGSDE_E_UNSUPPORTED;
+  const int stride_w = d->stride_w ? d->stride_w : d->stride;
+  if (stride_w != 1 && stride_w != 2) return SEGSDE_E_UNSUPPORTED;
   View v1 = mk(x1), v2 = mk(x2), vd = mk(dy);
   const int C1 = v1.c, C2 = v2.p ? v2.c : 0, Cout = vd.c;
   if (C1 % 32 || C2 % 32 || Cout % 32) return SEGSDE_E_UNSUPPORTED;
-  const int Ho = (v1.h + 2 * d->pad - d->dil * (d->kh - 1) - 1) / d->stride + 1, Wo = v1.w + 2 * d->pad - d->dil * (d->kw - 1);
+  const int Ho = (v1.h + 2 * d->pad - d->dil * (d->kh - 1) - 1) / d->stride + 1;
+  const int Wo = (v1.w + 2 * d->pad - d->dil * (d->kw - 1) - 1) / stride_w + 1;
   if (vd.h != Ho || vd.w != Wo || vd.n != v1.n) return SEGSDE_E_ARG;
   if (Wo % 32) return SEGSDE_E_UNSUPPORTED;
   const int BN = (Cout % 128 == 0) ? 128 : (Cout % 64 == 0 ? 64 : 32);
-  if (wg3_mode() && d->kh == 3 && d->kw == 3 && d->stride == 1 && BN >= 64 && 32 + 2 * d->dil <= 256) {
+  if (wg3_mode() && d->kh == 3 && d->kw == 3 && d->stride == 1 && stride_w == 1 && BN >= 64 && 32 + 2 * d->dil <= 256) {
     TcWg3P q;
     q.dw = dw; q.C[0] = C1; q.C[1] = C2; q.Ctot = C1 + C2; q.Cout = Cout; q.Ktot = 9 * q.Ctot;
     q.pad = d->pad; q.dil = d->dil; q.Ho = Ho; q.Wo = Wo; q.N = v1.n; q.wchunks = Wo / 32;
@@ -1048,7 +1051,7 @@ extern "C" int segsde_conv2d_wgrad_tc(const segsde_nhwc_t* x1, const segsde_nhwc
   }
   TcWgradP p;
   p.dw = dw; p.C[0] = C1; p.C[1] = C2; p.Ctot = C1 + C2; p.Cout = Cout; p.Ktot = d->kh * d->kw * p.Ctot;
-  p.kh = d->kh; p.kw = d->kw; p.pad = d->pad; p.dil = d->dil; p.stride_h = d->stride;
+  p.kh = d->kh; p.kw = d->kw; p.pad = d->pad; p.dil = d->dil; p.stride_h = d->stride; p.stride_w = stride_w;
   p.Ho = Ho; p.Wo = Wo; p.N = v1.n; p.wchunks = Wo / 32;
   p.chunks = (long long)p.N * Ho * p.wchunks;
   p.mtiles = cdiv(p.Ktot, 128); p.ntiles = Cout / BN;
@@ -1060,8 +1063,8 @@ extern "C" int segsde_conv2d_wgrad_tc(const segsde_nhwc_t* x1, const segsde_nhwc
   p.splits = (int)((p.chunks + p.chunks_per_split - 1) / p.chunks_per_split);
   CUtensorMap x0m, x1m, dym;
   const CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-  if (!make_act_map(&x0m, v1, 32, 1, 1, swz)) return SEGSDE_E_UNSUPPORTED;
-  if (C2) { if (!make_act_map(&x1m, v2, 32, 1, 1, swz)) return SEGSDE_E_UNSUPPORTED; } else x1m = x0m;
+  if (!make_act_map(&x0m, v1, 32, 1, 1, swz, stride_w)) return SEGSDE_E_UNSUPPORTED;
+  if (C2) { if (!make_act_map(&x1m, v2, 32, 1, 1, swz, stride_w)) return SEGSDE_E_UNSUPPORTED; } else x1m = x0m;
   if (!make_act_map(&dym, vd, 32, 1, 1, swz)) return SEGSDE_E_UNSUPPORTED;
   cudaStream_t st = as_stream(stream);
   if (BN == 128) return launch_wgrad<128>(x0m, x1m, dym, p, st);

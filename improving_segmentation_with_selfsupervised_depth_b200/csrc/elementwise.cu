@@ -436,6 +436,22 @@ extern "C" int segsde_bn_apply(const segsde_nhwc_t* x, const float* mean, const 
   DISPATCH_VEC(v4, bn_apply_kernel, vx, vx, mean, invstd, gamma, beta, vr, vy, act);
   return launched();
 }
+extern "C" int segsde_bn_apply_train(const segsde_nhwc_t* x, const double* sums, int64_t count, float eps, float momentum,
+                                     const float* gamma, const float* beta, const segsde_nhwc_t* residual,
+                                     const segsde_nhwc_t* y, int act, float* mean, float* invstd, float* running_mean,
+                                     float* running_var, void* stream) {
+  if (!x || !x->ptr || !y || !y->ptr || !sums || !mean || !invstd || count < 1) return SEGSDE_E_ARG;
+  if ((running_mean == nullptr) != (running_var == nullptr)) return SEGSDE_E_ARG;
+  View vx = mk(x), vy = mk(y), vr = mk(residual);
+  if (!same_shape(vx, vy) || (vr.p && !same_shape(vx, vr))) return SEGSDE_E_ARG;
+  if (act != SEGSDE_ACT_NONE && act != SEGSDE_ACT_RELU) return SEGSDE_E_UNSUPPORTED;
+  if (vx.c <= 2048 && pix_contig(vx) && pix_contig(vy) && (!vr.p || pix_contig(vr)))
+    return bn_apply_train_fast(vx, vr, vy, sums, count, eps, momentum, gamma, beta, act, mean, invstd, running_mean,
+                               running_var, as_stream(stream));
+  int rc = segsde_bn_finalize(sums, vx.c, count, eps, momentum, mean, invstd, running_mean, running_var, stream);
+  if (rc) return rc;
+  return segsde_bn_apply(x, mean, invstd, gamma, beta, residual, y, act, stream);
+}
 extern "C" int segsde_bn_bwd_reduce(const segsde_nhwc_t* x, const segsde_nhwc_t* y, const segsde_nhwc_t* dy,
                                     const float* mean, const float* invstd, int act, double* red, void* stream) {
   if (!x || !x->ptr || !dy || !dy->ptr || !mean || !invstd || !red) return SEGSDE_E_ARG;

@@ -74,7 +74,7 @@ def conv_bn(conv, bn, x, residual=None, act=A.ACT_NONE, **conv_kw):
     tensor-core epilogue (no separate pass over the conv output) when the BN layer normalises with batch statistics."""
     if (isinstance(bn, BatchNorm2d) and bn.uses_batch_stats() and isinstance(conv, Conv2d) and conv.bias is None
             and os.environ.get("SEGSDE_NO_BNFUSE", "0") != "1"):
-        sums = torch.zeros(3 * conv.out_channels, device=conv.weight.device, dtype=torch.float64)
+        sums = ops.zeros_f64(3 * conv.out_channels, conv.weight.device)
         return bn(conv(x, bn_stats=sums, **conv_kw), residual=residual, act=act, sums=sums)
     return bn(conv(x, **conv_kw), residual=residual, act=act)
 

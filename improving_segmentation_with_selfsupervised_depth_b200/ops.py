@@ -43,6 +43,26 @@ def cl_empty(n, c, h, w, device, zero=False):
     return f((n, h, w, c), device=device, dtype=torch.float32).permute(0, 3, 1, 2)
 
 
+_ZPOOL = {}
+_ZPOOL_CHUNK = 1 << 20      # float64 elements per pool chunk (8 MB)
+
+
+def zeros_f64(n, device):
+    """Zero-filled float64 accumulator (BatchNorm statistics / reductions) carved out of a pre-zeroed pool chunk:
+    one memset per ~1M elements instead of a fill kernel per layer.  Every slice is handed out exactly once; a
+    chunk is released by the allocator when its last slice dies."""
+    n_al = (n + 1) & ~1
+    if n_al > _ZPOOL_CHUNK // 4:
+        return torch.zeros(n, device=device, dtype=torch.float64)
+    st = _ZPOOL.get(device)
+    if st is None or st[1] + n_al > _ZPOOL_CHUNK:
+        st = [torch.zeros(_ZPOOL_CHUNK, device=device, dtype=torch.float64), 0]
+        _ZPOOL[device] = st
+    out = st[0][st[1]:st[1] + n]
+    st[1] += n_al
+    return out
+
+
 def is_cl(x):
     return x.dim() == 4 and (x.shape[1] == 1 or x.stride(1) == 1) and x.dtype == torch.float32
 
@@ -209,20 +229,23 @@ class _BatchNormFn(torch.autograd.Function):
         dev, st = x.device, A.stream_ptr()
         mean = torch.empty(c, device=dev, dtype=torch.float32)
         invstd = torch.empty(c, device=dev, dtype=torch.float32)
-        if training:
-            if sums is None:       # not already produced by the convolution epilogue
-                sums = torch.zeros(3 * c, device=dev, dtype=torch.float64)
-                A.call("segsde_bn_stats", C.byref(view(x)), A.ptr(sums), st)
-            A.call("segsde_bn_finalize", A.ptr(sums), C.c_int(c), C.c_int64(n * h * w), C.c_float(eps),
-                   C.c_float(momentum), A.ptr(mean), A.ptr(invstd), A.ptr(running_mean), A.ptr(running_var), st)
-        else:
-            A.call("segsde_bn_eval_prepare", A.ptr(running_mean), A.ptr(running_var), C.c_int(c), C.c_float(eps),
-                   A.ptr(mean), A.ptr(invstd), st)
         y = cl_empty(n, c, h, w, dev)
         gw = weight.detach() if weight is not None else None
         gb = bias.detach() if bias is not None else None
-        A.call("segsde_bn_apply", C.byref(view(x)), A.ptr(mean), A.ptr(invstd), A.ptr(gw), A.ptr(gb),
-               _ref(view(residual)) if residual is not None else None, C.byref(view(y)), C.c_int(act), st)
+        vres = _ref(view(residual)) if residual is not None else None
+        if training:
+            if sums is None:       # not already produced by the convolution epilogue
+                sums = zeros_f64(3 * c, dev)
+                A.call("segsde_bn_stats", C.byref(view(x)), A.ptr(sums), st)
+            # finalize (mean / invstd / running statistics) + normalise in one launch
+            A.call("segsde_bn_apply_train", C.byref(view(x)), A.ptr(sums), C.c_int64(n * h * w), C.c_float(eps),
+                   C.c_float(momentum), A.ptr(gw), A.ptr(gb), vres, C.byref(view(y)), C.c_int(act), A.ptr(mean),
+                   A.ptr(invstd), A.ptr(running_mean), A.ptr(running_var), st)
+        else:
+            A.call("segsde_bn_eval_prepare", A.ptr(running_mean), A.ptr(running_var), C.c_int(c), C.c_float(eps),
+                   A.ptr(mean), A.ptr(invstd), st)
+            A.call("segsde_bn_apply", C.byref(view(x)), A.ptr(mean), A.ptr(invstd), A.ptr(gw), A.ptr(gb), vres,
+                   C.byref(view(y)), C.c_int(act), st)
         ctx.save_for_backward(x, y if act == A.ACT_RELU else None, mean, invstd, gw)
         ctx.cfg = (training, act, residual is not None)
         return y
@@ -234,7 +257,7 @@ class _BatchNormFn(torch.autograd.Function):
         dy = as_cl(dy)
         n, c, h, w = x.shape
         dev, st = x.device, A.stream_ptr()
-        red = torch.zeros(2 * c, device=dev, dtype=torch.float64)
+        red = zeros_f64(2 * c, dev)
         vy = view(y) if y is not None else None
         A.call("segsde_bn_bwd_reduce", C.byref(view(x)), _ref(vy), C.byref(view(dy)), A.ptr(mean), A.ptr(invstd),
                C.c_int(act), A.ptr(red), st)

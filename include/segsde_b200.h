@@ -161,6 +161,14 @@ int segsde_bn_eval_prepare(const float* running_mean, const float* running_var, 
 int segsde_bn_apply(const segsde_nhwc_t* x, const float* mean, const float* invstd,
                     const float* gamma, const float* beta, const segsde_nhwc_t* residual,
                     const segsde_nhwc_t* y, int act, void* stream);
+/* Train-mode forward in one launch: segsde_bn_finalize (batch mean / invstd from `sums`, written to mean / invstd for
+ * the backward pass, running buffers updated when given) followed by segsde_bn_apply.  Every CTA derives the
+ * per-channel scale / shift from `sums` itself (fp64) into shared memory, CTA 0 also publishes mean / invstd and
+ * updates the running statistics (torch.nn.BatchNorm2d semantics: unbiased variance, momentum). */
+int segsde_bn_apply_train(const segsde_nhwc_t* x, const double* sums, int64_t count, float eps, float momentum,
+                          const float* gamma, const float* beta, const segsde_nhwc_t* residual,
+                          const segsde_nhwc_t* y, int act, float* mean, float* invstd, float* running_mean,
+                          float* running_var, void* stream);
 /* Backward, step 1: red[0..C)=sum dz, red[C..2C)=sum dz*xhat (fp64, zero-filled) where
  * dz = dy * relu'(y) (act==RELU needs y). */
 int segsde_bn_bwd_reduce(const segsde_nhwc_t* x, const segsde_nhwc_t* y, const segsde_nhwc_t* dy,

@@ -44,6 +44,11 @@ CASES = [
     (16, 0, 1, 3, 1, 1, 1, True, False, 3, True, 16, 24),
     (32, 0, 12, 1, 1, 0, 1, False, False, 0, True, 4, 8),
     (70, 0, 66, 3, 1, 1, 1, False, False, 0, False, 9, 9),
+    # 1x1 conv over a handful of pixels (ASPP image pooling, model_parts.py:28-40): warp-per-output kernel
+    (96, 0, 40, 1, 1, 0, 1, False, False, 1, True, 1, 1),
+    (200, 0, 24, 1, 1, 0, 1, False, False, 0, False, 2, 3),
+    # pose head shape class (pose_decoder.py:33): few output channels, many pixels -> finely split wgrad
+    (64, 0, 12, 1, 1, 0, 1, False, False, 0, True, 16, 32),
 ]
 
 
