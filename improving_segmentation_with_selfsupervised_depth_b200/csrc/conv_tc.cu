@@ -230,6 +230,9 @@ __device__ __forceinline__ void epilogue_chunks(uint32_t taddr0, int first, int 
 constexpr int STAGES = 5;
 constexpr int MAX_STAT_C = 2048;
 constexpr int A_BYTES = 128 * 128;        // 128 rows x 32 fp32
+constexpr int WSTAGES = 3;                // generic wgrad: 3 stages so that two CTAs share an SM (measured on the
+                                          // <=64-channel 3x3 wgrad: a second resident CTA hides the TMA round trip
+                                          // far better than a deeper pipeline in one CTA, 1.8 -> 1.15 ms)
 constexpr int NT = 256;                   // wgrad kernels: 4 epilogue warps
 constexpr int NT_CONV = 384;              // fprop / dgrad kernels: 8 epilogue warps (two per TMEM lane quarter)
 constexpr int EPI_WARPS = 8;
@@ -557,20 +560,20 @@ struct TcWgradP {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __launch_bounds__(NT, 2)
 tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1,
                 const __grid_constant__ CUtensorMap tmDy, const TcWgradP p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int B_BYTES = BN * 128;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
+  __shared__ __align__(8) uint64_t bars[2 * WSTAGES + 1];
   __shared__ uint32_t tmem_base_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]), tfull = smem_u32(&bars[2 * STAGES]);
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[WSTAGES]), tfull = smem_u32(&bars[2 * WSTAGES]);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+    for (int i = 0; i < WSTAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
     mbar_init(tfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&tmX0); tma_prefetch_desc(&tmDy);
@@ -622,7 +625,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant_
           tma_load_4d(sa + g * 4096, g_src[g] ? &tmX1 : &tmX0, fb, g_c[g], w0 * p.stride_w + g_dw[g], h * p.stride_h + g_dh[g], n);
 #pragma unroll
         for (int j = 0; j < BN / 32; ++j) tma_load_4d(sb + j * 4096, &tmDy, fb, nt * BN + j * 32, w0, h, n);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == WSTAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -642,7 +645,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant_
         if (it == niter - 1) tc_commit(tfull);
       }
       __syncwarp();
-      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      if (++stage == WSTAGES) { stage = 0; phase ^= 1; }
     }
   } else if (warp >= 4 && niter > 0) {
     const int q = warp - 4;
@@ -685,12 +688,14 @@ struct TcWg3P {
   int Ho, Wo, N;
   int wchunks; long long chunks;
   int groups0, groups;          // channel groups (<=128 ch) of source 0 / both sources
+  int units;                    // 3: one CTA per tap row.  2 (every group <= 64 channels): tap rows {0,1} share a
+                                // CTA — its four M groups are (row, 32-channel chunk) pairs — and row 2 has its own
   int ntiles, splits; long long chunks_per_split;
   int xbox;                     // bytes reserved per x box in smem
 };
 
-template <int BN, int NSTAGE>
-__global__ void __launch_bounds__(NT, 1)
+template <int BN, int NSTAGE, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 tc_wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1,
                    const __grid_constant__ CUtensorMap tmDy, const TcWg3P p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -721,12 +726,15 @@ tc_wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
   // tap row fastest, then channel group / output tile, pixel range slowest: the CTAs that stream the same pixels
   // (x and dY) are co-scheduled, so those tensors come from L2 instead of being re-read from DRAM per tap row
   int b = blockIdx.x;
-  const int r = b % 3; b /= 3;
+  const int unit = b % p.units; b /= p.units;
+  const bool paired = p.units == 2 && unit == 0;                   // this CTA accumulates tap rows 0 and 1
+  const int r = p.units == 2 ? unit * 2 : unit;                    // first tap row of this CTA
   const int grp = b % p.groups; b /= p.groups;
   const int nt = b % p.ntiles; const int split = b / p.ntiles;
   const int src = grp < p.groups0 ? 0 : 1;
   const int cbase = (src ? grp - p.groups0 : grp) * 128;           // within the source
-  const int ng = min(4, (p.C[src] - cbase) / 32);                  // valid 32-channel chunks in this group
+  const int nch = min(4, (p.C[src] - cbase) / 32);                 // valid 32-channel chunks in this group
+  const int ng = paired ? 2 * nch : nch;                           // M groups of 32 rows: (tap row, chunk) pairs
   const int cabs = (src ? p.C[0] : 0) + cbase;                     // channel offset in the concatenated K index
   const long long c_beg = (long long)split * p.chunks_per_split;
   const long long c_end = min(p.chunks, c_beg + p.chunks_per_split);
@@ -744,8 +752,10 @@ tc_wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
         const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes), sb = sa + 4 * p.xbox;
         const uint32_t fb = full0 + 8 * stage;
         mbar_expect_tx(fb, tx);
-        for (int g = 0; g < ng; ++g)
-          tma_load_4d(sa + g * p.xbox, src ? &tmX1 : &tmX0, fb, cbase + g * 32, w0 - p.pad, h - p.pad + r * p.dil, n);
+        for (int g = 0; g < ng; ++g) {
+          const int chunk = paired ? (g >> 1) : g, rr = paired ? r + (g & 1) : r;
+          tma_load_4d(sa + g * p.xbox, src ? &tmX1 : &tmX0, fb, cbase + chunk * 32, w0 - p.pad, h - p.pad + rr * p.dil, n);
+        }
 #pragma unroll
         for (int j = 0; j < BN / 32; ++j) tma_load_4d(sb + j * 4096, &tmDy, fb, nt * BN + j * 32, w0, h, n);
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
@@ -775,13 +785,15 @@ tc_wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
       if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
     }
   } else if (warp >= 4 && niter > 0) {
-    const int q = warp - 4;
+    const int q = warp - 4;                // = M group of this warp's 32 accumulator rows
     const int m = q * 32 + lane;
+    const int rr = paired ? r + (q & 1) : r;
+    const int ch = paired ? (q >> 1) * 32 + lane : m;
     mbar_wait(tfull, 0);
     tc_fence_after();
 #pragma unroll 1
     for (int s = 0; s < 3; ++s) {
-      const int kf = (r * 3 + s) * p.Ctot + cabs + m;
+      const int kf = (rr * 3 + s) * p.Ctot + cabs + ch;
 #pragma unroll 1
       for (int cc = 0; cc < BN / 32; ++cc) {
         float v[32];
@@ -870,7 +882,7 @@ static int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
 }
 template <int BN>
 static int launch_wgrad(const CUtensorMap& x0, const CUtensorMap& x1, const CUtensorMap& dy, const TcWgradP& p, cudaStream_t st) {
-  constexpr int smem = STAGES * (A_BYTES + BN * 128) + 1024;
+  constexpr int smem = WSTAGES * (A_BYTES + BN * 128) + 1024;
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(tc_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
   tc_wgrad_kernel<BN><<<p.mtiles * p.ntiles * p.splits, NT, smem, st>>>(x0, x1, dy, p);
@@ -903,24 +915,32 @@ static int rowhalo_mode() {
   return m;
 }
 
-template <int BN, int NSTAGE>
+template <int BN, int NSTAGE, int MINB>
 static int launch_wgrad3x3(const CUtensorMap& x0, const CUtensorMap& x1, const CUtensorMap& dy, const TcWg3P& p, cudaStream_t st) {
   const int smem = NSTAGE * (4 * p.xbox + BN * 128) + 1024;
   static int attr = 0;
   if (smem > 200 * 1024) return SEGSDE_E_UNSUPPORTED;
   if (smem > attr) {
-    if (cudaFuncSetAttribute(tc_wgrad3x3_kernel<BN, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(tc_wgrad3x3_kernel<BN, NSTAGE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       cudaGetLastError();
       return SEGSDE_E_UNSUPPORTED;
     }
     attr = smem;
   }
-  tc_wgrad3x3_kernel<BN, NSTAGE><<<p.groups * 3 * p.ntiles * p.splits, NT, smem, st>>>(x0, x1, dy, p);
+  tc_wgrad3x3_kernel<BN, NSTAGE, MINB><<<p.groups * p.units * p.ntiles * p.splits, NT, smem, st>>>(x0, x1, dy, p);
   return launched();
 }
 static int wg3_mode() {     // SEGSDE_TC_WGRAD3: 0 = off, 1 (default) = halo-reuse wgrad for 3x3 / stride 1
   static int m = -1;
   if (m < 0) { const char* e = getenv("SEGSDE_TC_WGRAD3"); m = e ? atoi(e) : 1; }
+  return m;
+}
+// SEGSDE_TC_WG64 (experiments on the <= 64-channel wgrad): bit 0 = pair tap rows 0/1 in one CTA (M = 2 x 64),
+// bit 1 = 3 stages with two CTAs per SM instead of 4 stages with one.  Default 3 (64->64 @512x1024, B=12:
+// 2.52 ms with neither, 1.82 pairing only, 1.55 two CTAs only, 1.15 ms with both).
+static int wg64_mode() {
+  static int m = -1;
+  if (m < 0) { const char* e = getenv("SEGSDE_TC_WG64"); m = e ? atoi(e) : 3; }
   return m;
 }
 
@@ -1033,7 +1053,8 @@ extern "C" int segsde_conv2d_wgrad_tc(const segsde_nhwc_t* x1, const segsde_nhwc
     q.groups0 = cdiv(C1, 128); q.groups = q.groups0 + (C2 ? cdiv(C2, 128) : 0);
     q.ntiles = Cout / BN;
     q.xbox = (((32 + 2 * d->dil) * 128) + 1023) / 1024 * 1024;
-    long long ctas = (long long)q.groups * 3 * q.ntiles;
+    q.units = ((wg64_mode() & 1) && C1 <= 64 && C2 <= 64) ? 2 : 3;
+    long long ctas = (long long)q.groups * q.units * q.ntiles;
     long long want = (2LL * num_sms()) / ctas; if (want < 1) want = 1;
     long long maxs = q.chunks / 16; if (maxs < 1) maxs = 1;
     q.splits = (int)(want < maxs ? want : maxs);
@@ -1044,8 +1065,14 @@ extern "C" int segsde_conv2d_wgrad_tc(const segsde_nhwc_t* x1, const segsde_nhwc
     if (make_act_map(&x0m, v1, 32 + 2 * d->dil, 1, 1, swz3) && (!C2 || make_act_map(&x1m, v2, 32 + 2 * d->dil, 1, 1, swz3)) &&
         make_act_map(&dym, vd, 32, 1, 1, swz3)) {
       if (!C2) x1m = x0m;
-      int rc = BN == 128 ? launch_wgrad3x3<128, 3>(x0m, x1m, dym, q, as_stream(stream))
-                         : launch_wgrad3x3<64, 4>(x0m, x1m, dym, q, as_stream(stream));
+      int rc;
+      if (BN == 128) {     // TMEM (3 x 128 columns) allows one CTA per SM: as many stages as shared memory holds
+        rc = launch_wgrad3x3<128, 5, 1>(x0m, x1m, dym, q, as_stream(stream));
+        if (rc == SEGSDE_E_UNSUPPORTED) rc = launch_wgrad3x3<128, 3, 1>(x0m, x1m, dym, q, as_stream(stream));
+      } else {
+        rc = (wg64_mode() & 2) ? launch_wgrad3x3<64, 3, 2>(x0m, x1m, dym, q, as_stream(stream))
+                               : launch_wgrad3x3<64, 4, 1>(x0m, x1m, dym, q, as_stream(stream));
+      }
       if (rc != SEGSDE_E_UNSUPPORTED) return rc;
     }
   }
@@ -1055,7 +1082,7 @@ extern "C" int segsde_conv2d_wgrad_tc(const segsde_nhwc_t* x1, const segsde_nhwc
   p.Ho = Ho; p.Wo = Wo; p.N = v1.n; p.wchunks = Wo / 32;
   p.chunks = (long long)p.N * Ho * p.wchunks;
   p.mtiles = cdiv(p.Ktot, 128); p.ntiles = Cout / BN;
-  long long want = (2LL * num_sms()) / ((long long)p.mtiles * p.ntiles);
+  long long want = (4LL * num_sms()) / ((long long)p.mtiles * p.ntiles);
   if (want < 1) want = 1;
   long long maxs = p.chunks / 16; if (maxs < 1) maxs = 1;
   p.splits = (int)(want < maxs ? want : maxs);
