@@ -51,6 +51,12 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -293,6 +299,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
   if (warp == 0) {
     // ===================== TMA producer =====================
+    // (splitting the activation / weight copies over two issuing warps was measured and does not help here: the
+    // fprop kernels are bound by L2 -> SM bandwidth, not by the issue rate of the bulk copies, unlike wgrad)
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
@@ -552,6 +560,8 @@ struct TcWgradP {
   int C[2], Ctot, Cout, Ktot;
   int kh, kw, pad, dil;
   int stride_h, stride_w;     // strides of the convolution (the x boxes use TMA element strides horizontally)
+  int xmerge, chb, rhb;       // xmerge: the x operand comes through the 5-D map in boxes of chb chunks x rhb rows
+                              // (= chb*rhb consecutive 32-row M groups per bulk copy); 0: one 4-D copy per group
   int Ho, Wo, N;
   int wchunks;                // Wo / 32
   long long chunks;           // N * Ho * wchunks
@@ -562,7 +572,7 @@ struct TcWgradP {
 template <int BN>
 __global__ void __launch_bounds__(NT, 2)
 tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1,
-                const __grid_constant__ CUtensorMap tmDy, const TcWgradP p) {
+                const __grid_constant__ CUtensorMap tmX5, const __grid_constant__ CUtensorMap tmDy, const TcWgradP p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int B_BYTES = BN * 128;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -576,7 +586,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant_
     for (int i = 0; i < WSTAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
     mbar_init(tfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    tma_prefetch_desc(&tmX0); tma_prefetch_desc(&tmDy);
+    tma_prefetch_desc(p.xmerge ? &tmX5 : &tmX0); tma_prefetch_desc(&tmDy);
     if (p.C[1]) tma_prefetch_desc(&tmX1);
   }
   if (warp == 2) {
@@ -620,11 +630,20 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant_
         mbar_wait(empty0 + 8 * stage, phase ^ 1);
         const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES), sb = sa + A_BYTES;
         const uint32_t fb = full0 + 8 * stage;
-        mbar_expect_tx(fb, (ngroups + BN / 32) * 4096);
-        for (int g = 0; g < ngroups; ++g)
-          tma_load_4d(sa + g * 4096, g_src[g] ? &tmX1 : &tmX0, fb, g_c[g], w0 * p.stride_w + g_dw[g], h * p.stride_h + g_dh[g], n);
-#pragma unroll
-        for (int j = 0; j < BN / 32; ++j) tma_load_4d(sb + j * 4096, &tmDy, fb, nt * BN + j * 32, w0, h, n);
+        if (p.xmerge) {
+          const int per = p.chb * p.rhb;                      // M groups per bulk copy (a full box always lands)
+          const int nload = (ngroups + per - 1) / per;
+          mbar_expect_tx(fb, (nload * per + BN / 32) * 4096);
+          for (int l = 0; l < nload; ++l) {
+            const int g = l * per;
+            tma_load_5d(sa + g * 4096, &tmX5, fb, 0, w0 * p.stride_w + g_dw[g], g_c[g] >> 5, h * p.stride_h + g_dh[g], n);
+          }
+        } else {
+          mbar_expect_tx(fb, (ngroups + BN / 32) * 4096);
+          for (int g = 0; g < ngroups; ++g)
+            tma_load_4d(sa + g * 4096, g_src[g] ? &tmX1 : &tmX0, fb, g_c[g], w0 * p.stride_w + g_dw[g], h * p.stride_h + g_dh[g], n);
+        }
+        tma_load_5d(sb, &tmDy, fb, 0, w0, nt * (BN / 32), h, n);     // all BN/32 output-channel chunks in one copy
         if (++stage == WSTAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -691,12 +710,15 @@ struct TcWg3P {
   int units;                    // 3: one CTA per tap row.  2 (every group <= 64 channels): tap rows {0,1} share a
                                 // CTA — its four M groups are (row, 32-channel chunk) pairs — and row 2 has its own
   int ntiles, splits; long long chunks_per_split;
-  int xbox;                     // bytes reserved per x box in smem
+  int xbox;                     // bytes reserved per 32-channel x box in a stage (1 KB multiple)
+  int merge;                    // 1: 5-D maps - one bulk copy brings all (tap row, chunk) groups of a stage, packed
+                                // at (32 + 2*dil) * 128 bytes per group; 0: one 4-D copy per group at xbox strides
 };
 
 template <int BN, int NSTAGE, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
 tc_wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1,
+                   const __grid_constant__ CUtensorMap tmX0p, const __grid_constant__ CUtensorMap tmX1p,
                    const __grid_constant__ CUtensorMap tmDy, const TcWg3P p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int B_BYTES = BN * 128;
@@ -713,6 +735,7 @@ tc_wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&tmX0); tma_prefetch_desc(&tmDy);
     if (p.C[1]) tma_prefetch_desc(&tmX1);
+    if (p.units == 2) tma_prefetch_desc(&tmX0p);
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(TCOLS));
@@ -739,11 +762,15 @@ tc_wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
   const long long c_beg = (long long)split * p.chunks_per_split;
   const long long c_end = min(p.chunks, c_beg + p.chunks_per_split);
   const int niter = (int)max(0LL, c_end - c_beg);
+  // merged copies pack the M groups as [tap row][chunk] at the exact box pitch; the per-group form keeps xbox strides
+  const uint32_t bx = (uint32_t)((32 + 2 * p.dil) * 128);
+  const uint32_t gstride = p.merge ? bx : (uint32_t)p.xbox;
+  const int nbox_ch = min(4, p.C[src] / 32);                       // chunks per merged box of this source's map
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      const uint32_t tx = (uint32_t)ng * (uint32_t)((32 + 2 * p.dil) * 128) + (BN / 32) * 4096u;
+      const uint32_t tx = (p.merge ? (uint32_t)(nbox_ch * (paired ? 2 : 1)) : (uint32_t)ng) * bx + (BN / 32) * 4096u;
       for (long long ch = c_beg; ch < c_end; ++ch) {
         const int wc = (int)(ch % p.wchunks); long long q = ch / p.wchunks;
         const int h = (int)(q % p.Ho); const int n = (int)(q / p.Ho);
@@ -752,12 +779,16 @@ tc_wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
         const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes), sb = sa + 4 * p.xbox;
         const uint32_t fb = full0 + 8 * stage;
         mbar_expect_tx(fb, tx);
-        for (int g = 0; g < ng; ++g) {
-          const int chunk = paired ? (g >> 1) : g, rr = paired ? r + (g & 1) : r;
-          tma_load_4d(sa + g * p.xbox, src ? &tmX1 : &tmX0, fb, cbase + chunk * 32, w0 - p.pad, h - p.pad + rr * p.dil, n);
+        if (p.merge) {
+          const CUtensorMap* xm = paired ? (src ? &tmX1p : &tmX0p) : (src ? &tmX1 : &tmX0);
+          tma_load_5d(sa, xm, fb, 0, w0 - p.pad, cbase >> 5, h - p.pad + r * p.dil, n);
+        } else {
+          for (int g = 0; g < ng; ++g) {
+            const int chunk = paired ? g % nch : g, rr = paired ? r + g / nch : r;
+            tma_load_4d(sa + g * p.xbox, src ? &tmX1 : &tmX0, fb, cbase + chunk * 32, w0 - p.pad, h - p.pad + rr * p.dil, n);
+          }
         }
-#pragma unroll
-        for (int j = 0; j < BN / 32; ++j) tma_load_4d(sb + j * 4096, &tmDy, fb, nt * BN + j * 32, w0, h, n);
+        tma_load_5d(sb, &tmDy, fb, 0, w0, nt * (BN / 32), h, n);
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
       }
     }
@@ -773,7 +804,7 @@ tc_wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
         for (int s = 0; s < 3; ++s) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint64_t ad = make_desc(sa + s * p.dil * 128 + 1024 * k, p.xbox, 512, 1);
+            const uint64_t ad = make_desc(sa + s * p.dil * 128 + 1024 * k, gstride, 512, 1);
             const uint64_t bd = make_desc(sb + 1024 * k, 4096, 512, 1);
             tc_mma_tf32(tmem_base + s * BN, ad, bd, idesc, (it | k) != 0);
           }
@@ -787,8 +818,8 @@ tc_wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
   } else if (warp >= 4 && niter > 0) {
     const int q = warp - 4;                // = M group of this warp's 32 accumulator rows
     const int m = q * 32 + lane;
-    const int rr = paired ? r + (q & 1) : r;
-    const int ch = paired ? (q >> 1) * 32 + lane : m;
+    const int rr = paired ? r + q / nch : r;
+    const int ch = paired ? (q % nch) * 32 + lane : m;
     mbar_wait(tfull, 0);
     tc_fence_after();
 #pragma unroll 1
@@ -847,6 +878,21 @@ static bool make_act_map(CUtensorMap* m, const View& v, int bw, int bh, int estr
                         swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
+// NHWC activation view -> 5-D map (32 ch, W, C/32, H, N), box (32, bw, nchi, bh, 1): ONE bulk copy lands nchi
+// 32-channel chunks x bh image rows as consecutive [row][chunk][pixel][32 ch] groups of bw*128 bytes — the MN-major
+// operand layout of the wgrad kernels, which used to take one copy per chunk (the single producer thread was the
+// bottleneck: 6-8 bulk copies per 12 MMAs).
+static bool make_act_map5(CUtensorMap* m, const View& v, int bw, int bh, int nchi, CUtensorMapSwizzle swz, int estride_w = 1) {
+  if ((reinterpret_cast<uintptr_t>(v.p) & 15) || (v.sw % 4) || (v.sh % 4) || (v.sn % 4) || (v.c % 32)) return false;
+  cuuint64_t dims[5] = {32, (cuuint64_t)v.w, (cuuint64_t)(v.c / 32), (cuuint64_t)v.h, (cuuint64_t)v.n};
+  cuuint64_t strides[4] = {(cuuint64_t)v.sw * 4, 128, (cuuint64_t)v.sh * 4, (cuuint64_t)v.sn * 4};
+  cuuint32_t box[5] = {32, (cuuint32_t)(bw * estride_w), (cuuint32_t)nchi, (cuuint32_t)bh, 1};
+  cuuint32_t es[5] = {1, (cuuint32_t)estride_w, 1, 1, 1};
+  if (box[1] > 256 || box[2] > 256 || box[3] > 256) return false;
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, v.p, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
 static bool make_w_map(CUtensorMap* m, const float* w, int ktot, int cout, int bn) {
   if ((reinterpret_cast<uintptr_t>(w) & 15) || (ktot % 4)) return false;
   cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)cout};
@@ -881,11 +927,12 @@ static int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
   return launched();
 }
 template <int BN>
-static int launch_wgrad(const CUtensorMap& x0, const CUtensorMap& x1, const CUtensorMap& dy, const TcWgradP& p, cudaStream_t st) {
+static int launch_wgrad(const CUtensorMap& x0, const CUtensorMap& x1, const CUtensorMap& x5, const CUtensorMap& dy,
+                        const TcWgradP& p, cudaStream_t st) {
   constexpr int smem = WSTAGES * (A_BYTES + BN * 128) + 1024;
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(tc_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
-  tc_wgrad_kernel<BN><<<p.mtiles * p.ntiles * p.splits, NT, smem, st>>>(x0, x1, dy, p);
+  tc_wgrad_kernel<BN><<<p.mtiles * p.ntiles * p.splits, NT, smem, st>>>(x0, x1, x5, dy, p);
   return launched();
 }
 
@@ -916,7 +963,8 @@ static int rowhalo_mode() {
 }
 
 template <int BN, int NSTAGE, int MINB>
-static int launch_wgrad3x3(const CUtensorMap& x0, const CUtensorMap& x1, const CUtensorMap& dy, const TcWg3P& p, cudaStream_t st) {
+static int launch_wgrad3x3(const CUtensorMap& x0, const CUtensorMap& x1, const CUtensorMap& x0p, const CUtensorMap& x1p,
+                           const CUtensorMap& dy, const TcWg3P& p, cudaStream_t st) {
   const int smem = NSTAGE * (4 * p.xbox + BN * 128) + 1024;
   static int attr = 0;
   if (smem > 200 * 1024) return SEGSDE_E_UNSUPPORTED;
@@ -927,7 +975,7 @@ static int launch_wgrad3x3(const CUtensorMap& x0, const CUtensorMap& x1, const C
     }
     attr = smem;
   }
-  tc_wgrad3x3_kernel<BN, NSTAGE, MINB><<<p.groups * p.units * p.ntiles * p.splits, NT, smem, st>>>(x0, x1, dy, p);
+  tc_wgrad3x3_kernel<BN, NSTAGE, MINB><<<p.groups * p.units * p.ntiles * p.splits, NT, smem, st>>>(x0, x1, x0p, x1p, dy, p);
   return launched();
 }
 static int wg3_mode() {     // SEGSDE_TC_WGRAD3: 0 = off, 1 (default) = halo-reuse wgrad for 3x3 / stride 1
@@ -938,6 +986,11 @@ static int wg3_mode() {     // SEGSDE_TC_WGRAD3: 0 = off, 1 (default) = halo-reu
 // SEGSDE_TC_WG64 (experiments on the <= 64-channel wgrad): bit 0 = pair tap rows 0/1 in one CTA (M = 2 x 64),
 // bit 1 = 3 stages with two CTAs per SM instead of 4 stages with one.  Default 3 (64->64 @512x1024, B=12:
 // 2.52 ms with neither, 1.82 pairing only, 1.55 two CTAs only, 1.15 ms with both).
+static int wgmerge_mode() {   // SEGSDE_TC_WGMERGE: 0 = one bulk copy per 32-channel chunk (round-1 form), 1 (default) = merged
+  static int m = -1;
+  if (m < 0) { const char* e = getenv("SEGSDE_TC_WGMERGE"); m = e ? atoi(e) : 1; }
+  return m;
+}
 static int wg64_mode() {
   static int m = -1;
   if (m < 0) { const char* e = getenv("SEGSDE_TC_WG64"); m = e ? atoi(e) : 3; }
@@ -1053,25 +1106,36 @@ extern "C" int segsde_conv2d_wgrad_tc(const segsde_nhwc_t* x1, const segsde_nhwc
     q.groups0 = cdiv(C1, 128); q.groups = q.groups0 + (C2 ? cdiv(C2, 128) : 0);
     q.ntiles = Cout / BN;
     q.xbox = (((32 + 2 * d->dil) * 128) + 1023) / 1024 * 1024;
-    q.units = ((wg64_mode() & 1) && C1 <= 64 && C2 <= 64) ? 2 : 3;
+    q.units = ((wg64_mode() & 1) && C1 <= 64 && C2 <= 64 && d->dil == 1) ? 2 : 3;
     long long ctas = (long long)q.groups * q.units * q.ntiles;
     long long want = (2LL * num_sms()) / ctas; if (want < 1) want = 1;
     long long maxs = q.chunks / 16; if (maxs < 1) maxs = 1;
     q.splits = (int)(want < maxs ? want : maxs);
     q.chunks_per_split = (q.chunks + q.splits - 1) / q.splits;
     q.splits = (int)((q.chunks + q.chunks_per_split - 1) / q.chunks_per_split);
-    CUtensorMap x0m, x1m, dym;
+    CUtensorMap x0m, x1m, x0p, x1p, dym;
     const CUtensorMapSwizzle swz3 = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-    if (make_act_map(&x0m, v1, 32 + 2 * d->dil, 1, 1, swz3) && (!C2 || make_act_map(&x1m, v2, 32 + 2 * d->dil, 1, 1, swz3)) &&
-        make_act_map(&dym, vd, 32, 1, 1, swz3)) {
+    const int bw = 32 + 2 * d->dil;
+    const int ch1 = C1 / 32 < 4 ? C1 / 32 : 4, ch2 = C2 ? (C2 / 32 < 4 ? C2 / 32 : 4) : 0;
+    bool ok;
+    q.merge = wgmerge_mode();
+    if (q.merge) {
+      ok = make_act_map5(&x0m, v1, bw, 1, ch1, swz3) && (!C2 || make_act_map5(&x1m, v2, bw, 1, ch2, swz3));
+      if (ok && q.units == 2) ok = make_act_map5(&x0p, v1, bw, 2, ch1, swz3) && (!C2 || make_act_map5(&x1p, v2, bw, 2, ch2, swz3));
+    } else {
+      ok = make_act_map(&x0m, v1, bw, 1, 1, swz3) && (!C2 || make_act_map(&x1m, v2, bw, 1, 1, swz3));
+    }
+    if (ok && make_act_map5(&dym, vd, 32, 1, BN / 32, swz3)) {
       if (!C2) x1m = x0m;
+      if (!(q.merge && q.units == 2)) { x0p = x0m; x1p = x1m; } else if (!C2) x1p = x0p;
+      cudaStream_t st3 = as_stream(stream);
       int rc;
       if (BN == 128) {     // TMEM (3 x 128 columns) allows one CTA per SM: as many stages as shared memory holds
-        rc = launch_wgrad3x3<128, 5, 1>(x0m, x1m, dym, q, as_stream(stream));
-        if (rc == SEGSDE_E_UNSUPPORTED) rc = launch_wgrad3x3<128, 3, 1>(x0m, x1m, dym, q, as_stream(stream));
+        rc = launch_wgrad3x3<128, 5, 1>(x0m, x1m, x0p, x1p, dym, q, st3);
+        if (rc == SEGSDE_E_UNSUPPORTED) rc = launch_wgrad3x3<128, 3, 1>(x0m, x1m, x0p, x1p, dym, q, st3);
       } else {
-        rc = (wg64_mode() & 2) ? launch_wgrad3x3<64, 3, 2>(x0m, x1m, dym, q, as_stream(stream))
-                               : launch_wgrad3x3<64, 4, 1>(x0m, x1m, dym, q, as_stream(stream));
+        rc = (wg64_mode() & 2) ? launch_wgrad3x3<64, 3, 2>(x0m, x1m, x0p, x1p, dym, q, st3)
+                               : launch_wgrad3x3<64, 4, 1>(x0m, x1m, x0p, x1p, dym, q, st3);
       }
       if (rc != SEGSDE_E_UNSUPPORTED) return rc;
     }
@@ -1088,13 +1152,24 @@ extern "C" int segsde_conv2d_wgrad_tc(const segsde_nhwc_t* x1, const segsde_nhwc
   p.splits = (int)(want < maxs ? want : maxs);
   p.chunks_per_split = (p.chunks + p.splits - 1) / p.splits;
   p.splits = (int)((p.chunks + p.chunks_per_split - 1) / p.chunks_per_split);
-  CUtensorMap x0m, x1m, dym;
+  CUtensorMap x0m, x1m, x5m, dym;
   const CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   if (!make_act_map(&x0m, v1, 32, 1, 1, swz, stride_w)) return SEGSDE_E_UNSUPPORTED;
   if (C2) { if (!make_act_map(&x1m, v2, 32, 1, 1, swz, stride_w)) return SEGSDE_E_UNSUPPORTED; } else x1m = x0m;
-  if (!make_act_map(&dym, vd, 32, 1, 1, swz)) return SEGSDE_E_UNSUPPORTED;
+  // merged x copies (single source): chb consecutive chunks of one tap, and - when the taps of an M tile are
+  // vertically consecutive rows (kw == 1, dil == 1: the stem band) - rhb tap rows per bulk copy
+  p.xmerge = 0; p.chb = p.rhb = 1;
+  x5m = x0m;
+  if (!C2 && wgmerge_mode()) {
+    const int nch = C1 / 32;
+    p.chb = nch % 4 == 0 ? 4 : (nch % 2 == 0 ? 2 : 1);
+    p.rhb = (nch == p.chb && d->kw == 1 && d->dil == 1) ? 4 / p.chb : 1;
+    if (p.chb * p.rhb > 1 && make_act_map5(&x5m, v1, 32, p.rhb, p.chb, swz, stride_w)) p.xmerge = 1;
+    else { p.chb = p.rhb = 1; x5m = x0m; }
+  }
+  if (!make_act_map5(&dym, vd, 32, 1, BN / 32, swz)) return SEGSDE_E_UNSUPPORTED;
   cudaStream_t st = as_stream(stream);
-  if (BN == 128) return launch_wgrad<128>(x0m, x1m, dym, p, st);
-  if (BN == 64) return launch_wgrad<64>(x0m, x1m, dym, p, st);
-  return launch_wgrad<32>(x0m, x1m, dym, p, st);
+  if (BN == 128) return launch_wgrad<128>(x0m, x1m, x5m, dym, p, st);
+  if (BN == 64) return launch_wgrad<64>(x0m, x1m, x5m, dym, p, st);
+  return launch_wgrad<32>(x0m, x1m, x5m, dym, p, st);
 }
