@@ -188,6 +188,9 @@ def run_b200(args):
     host = {k: v.pin_memory() for k, v in synthetic_inputs(B, H, W, seed=1234 + rank).items()}
     resident = {k: v.to(dev) for k, v in host.items()}
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+    # end-to-end arm: two device buffer sets filled from pinned host memory by a copy stream (double buffering)
+    copy_stream = torch.cuda.Stream(device=dev)
+    dev_bufs = [{k: torch.empty_like(v, device=dev) for k, v in host.items()} for _ in range(2)]
 
     def step(inputs):
         if sync is not None:
@@ -215,25 +218,29 @@ def run_b200(args):
         last = None
         if e2e:
             # every step's inputs travel pinned host -> device inside the timed region; the copy of step i+1 is
-            # issued on a side stream while step i computes (double buffering), the loss is read back every step
-            copy_stream = torch.cuda.Stream(device=dev)
+            # issued on a side stream into the other of two preallocated device buffer sets while step i computes
+            # (no allocation inside the loop: a cudaMalloc there synchronises the device), the loss is read back
+            # every step
             main = torch.cuda.current_stream()
+            uploaded = [torch.cuda.Event(), torch.cuda.Event()]
+            consumed = [torch.cuda.Event(), torch.cuda.Event()]
 
-            def upload():
+            def upload(slot, first_use):
                 with torch.cuda.stream(copy_stream):
-                    bufs = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-                    ev = torch.cuda.Event()
-                    ev.record(copy_stream)
-                return bufs, ev
-            nxt = upload()
+                    if not first_use:
+                        copy_stream.wait_event(consumed[slot])      # the step that read this buffer set is done
+                    for k, v in host.items():
+                        dev_bufs[slot][k].copy_(v, non_blocking=True)
+                    uploaded[slot].record(copy_stream)
+            upload(0, True)
             for i in range(nsteps):
-                inputs, ev = nxt
-                main.wait_event(ev)
+                slot = i & 1
+                main.wait_event(uploaded[slot])
                 if i + 1 < nsteps:
-                    nxt = upload()
-                for v in inputs.values():
-                    v.record_stream(main)
-                last = step(inputs).item()          # D2H read of the step's loss
+                    upload(slot ^ 1, i == 0)
+                loss_t = step(dev_bufs[slot])
+                consumed[slot].record(main)
+                last = loss_t.item()                # D2H read of the step's loss
         else:
             for _ in range(nsteps):
                 last = step(resident)
@@ -248,6 +255,7 @@ def run_b200(args):
     with contextlib.redirect_stdout(io.StringIO()):
         for _ in range(max(args.warmup, 3)):
             step(resident)
+        timed(2, e2e=True)          # the host-buffer path is warmed up as well (untimed)
     torch.cuda.synchronize()
     clocks = ClockSampler(local)
     if rank == 0:
