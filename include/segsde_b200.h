@@ -133,6 +133,15 @@ int segsde_stem_pack_w(float* w, float* wp, int cout, int kh, int kw, int cin, i
 int segsde_head_stencil_fwd(const segsde_nhwc_t* z, const segsde_nhwc_t* y, const float* bias, int act, int reflect,
                             int pad, void* stream);
 int segsde_head_gcol(const segsde_nhwc_t* dy, const segsde_nhwc_t* gcol, int reflect, int pad, void* stream);
+/* The same heads in single-pass CUDA-core kernels that read x / write dx exactly once (the heads are HBM-bound:
+ * 18*C flops per 4*C input bytes) — C a multiple of 64, pad 1, w = [9][C] (OHWI with O = 1):
+ *   fwd  : y = act(bias + conv3x3(x, w)), tap planes kept in shared memory;
+ *   dgrad: dx = conv3x3^T(dz, w) incl. the reflection-padding adjoint (dz = gradient w.r.t. the pre-activation);
+ *   wgrad: dw[9][C] += sum_pixels g (x) x  (dw zero-filled or holding a running gradient). */
+int segsde_head_fwd_fused(const segsde_nhwc_t* x, const float* w, const float* bias, const segsde_nhwc_t* y, int act,
+                          int reflect, void* stream);
+int segsde_head_dgrad_fused(const segsde_nhwc_t* dz, const float* w, const segsde_nhwc_t* dx, int reflect, void* stream);
+int segsde_head_wgrad_fused(const segsde_nhwc_t* x, const segsde_nhwc_t* dz, float* dw, int reflect, void* stream);
 /* 1 if this process can run the tensor-core path (driver entry point for tensor maps found). */
 int segsde_tc_available(void);
 
