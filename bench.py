@@ -124,7 +124,7 @@ def cpu_step_factory(B, H, W):
                                 {f: out[("cam_T_cam", 0, f)] for f in (-1, 1)}, [0, -1, 1], H, W, noise=noise)["loss"]
         loss.backward()
         opt.step()
-        return float(loss)
+        return float(loss.detach())
     return step
 
 
@@ -333,7 +333,7 @@ def run_b200(args):
         "e2e": {"value": gb * args.steps / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches, "clocks": clk, "roofline": roof, "roofline_hbm_kernel": roof_hbm, "cpu_baseline": cpu,
-        "loss": float(last), "conv_roofline_frac_whole_step": FWD_GF_TRAIN_PER_SAMPLE * 1e9 * gb * args.steps
+        "loss": float(last.detach()) if hasattr(last, "detach") else float(last), "conv_roofline_frac_whole_step": FWD_GF_TRAIN_PER_SAMPLE * 1e9 * gb * args.steps
         / (ms * 1e-3) / 1e12 / peak_tf / world,
     }
     print(json.dumps(out))
