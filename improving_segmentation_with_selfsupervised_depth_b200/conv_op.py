@@ -115,7 +115,7 @@ class _Conv2dFn(torch.autograd.Function):
         dy = ops.as_cl(dy)
         need1, need2, needw, needb = ctx.needs_input_grad[:4]
         dev = dy.device
-        db = torch.zeros(cout, device=dev, dtype=torch.float32) if (has_bias and needb) else None
+        db = ops.zeros_f32(cout, dev) if (has_bias and needb) else None
         if act != A.ACT_NONE or db is not None:
             dz = ops.cl_empty(*dy.shape, dev) if act != A.ACT_NONE else None
             A.call("segsde_act_bwd_bias", ops._ref(ops.view(y)) if y is not None else None, C.byref(ops.view(dy)),
@@ -198,7 +198,7 @@ class _Conv2dFn(torch.autograd.Function):
 
         # ---- wgrad --------------------------------------------------------------------------------------
         if needw:
-            dw = torch.zeros_like(w)
+            dw = ops.zeros_like_w(w)
             v1, v2 = ops.view(x1e), (ops.view(x2e) if x2e is not None else None)
             if nchw:
                 v1.sn = v1.sh = v1.sw = 0
@@ -301,7 +301,7 @@ class _StemConvFn(torch.autograd.Function):
         if mode == "band":
             n, hp, wo, wp, P, kh, kw, ctot = geo
             band = _band_view(src, n, hp, wo, wp, P)
-            dwp = torch.zeros(cout * kh * 8 * P, device=dy.device, dtype=torch.float32)
+            dwp = ops.zeros_f32(cout * kh * 8 * P, dy.device)
             d = ops._desc(kh, 1, 2, 0, 1, A.PAD_ZERO, False, A.ACT_NONE, False, stride_w=1)
             ops._timed("wgrad", flops, lambda: A.call("segsde_conv2d_wgrad_tc", C.byref(band), None, C.byref(vdz), A.ptr(dwp),
                                                       None, C.byref(d), st), desc)
@@ -346,7 +346,7 @@ class _HeadConvFn(torch.autograd.Function):
             ctx.save_for_backward(x, w, None, y if act != A.ACT_NONE else None)
             ctx.cfg = (reflect, act, bias is not None, desc)
             return y
-        wz = torch.zeros(32 * c, device=dev, dtype=torch.float32)
+        wz = ops.zeros_f32(32 * c, dev)
         A.call("segsde_copy_rows", A.ptr(w), C.c_int(c), A.ptr(wz), C.c_int(c), C.c_int(9), C.c_int(c), st)
         z = ops.cl_empty(n, 32, h, wd, dev)
         d1 = ops._desc(1, 1, 1, 0, 1, A.PAD_ZERO, False, A.ACT_NONE, False)
@@ -366,7 +366,7 @@ class _HeadConvFn(torch.autograd.Function):
         dev, st = x.device, A.stream_ptr()
         dy = ops.as_cl(dy)
         need_x, need_w, need_b = ctx.needs_input_grad[:3]
-        db = torch.zeros(1, device=dev, dtype=torch.float32) if (has_bias and need_b) else None
+        db = ops.zeros_f32(1, dev) if (has_bias and need_b) else None
         if act != A.ACT_NONE or db is not None:
             dz = ops.cl_empty(*dy.shape, dev) if act != A.ACT_NONE else None
             A.call("segsde_act_bwd_bias", ops._ref(ops.view(y)) if y is not None else None, C.byref(ops.view(dy)),
@@ -383,7 +383,7 @@ class _HeadConvFn(torch.autograd.Function):
                 ops._timed("dgrad", flops, lambda: A.call("segsde_head_dgrad_fused", C.byref(vdz), A.ptr(w),
                                                           C.byref(ops.view(dx)), C.c_int(reflect), st), desc)
             if need_w:
-                dw = torch.zeros_like(w)
+                dw = ops.zeros_like_w(w)
                 ops._timed("wgrad", flops, lambda: A.call("segsde_head_wgrad_fused", C.byref(ops.view(x)), C.byref(vdz),
                                                           A.ptr(dw), C.c_int(reflect), st), desc)
             return dx, dw, db, None, None
@@ -398,7 +398,7 @@ class _HeadConvFn(torch.autograd.Function):
                 dx = ops.cl_empty(n, c, h, wd, dev)
                 _fwd(gcol, None, wzt, None, dx, d1, "dgrad", 2.0 * n * h * wd * 9 * c, desc)
             if need_w:
-                dwz = torch.zeros(32 * c, device=dev, dtype=torch.float32)
+                dwz = ops.zeros_f32(32 * c, dev)
                 v1, vg = ops.view(x), ops.view(gcol)
 
                 def launch_w():

@@ -63,6 +63,32 @@ def zeros_f64(n, device):
     return out
 
 
+_ZPOOL32 = {}
+_ZPOOL32_CHUNK = 1 << 25    # float32 elements per pool chunk (128 MB): about one training step's weight gradients
+
+
+def zeros_f32(n, device):
+    """Zero-filled float32 accumulator (weight / bias / BatchNorm-parameter gradients, which the kernels build with
+    atomics) carved out of a pre-zeroed pool chunk — the ~200 per-layer fill kernels of a training step become
+    one memset.  Slices are 256-byte aligned and handed out once; a chunk is released when its last slice dies."""
+    n_al = (n + 63) & ~63
+    if n_al > _ZPOOL32_CHUNK // 4:
+        return torch.zeros(n, device=device, dtype=torch.float32)
+    st = _ZPOOL32.get(device)
+    if st is None or st[1] + n_al > _ZPOOL32_CHUNK:
+        st = [torch.zeros(_ZPOOL32_CHUNK, device=device, dtype=torch.float32), 0]
+        _ZPOOL32[device] = st
+    out = st[0][st[1]:st[1] + n]
+    st[1] += n_al
+    return out
+
+
+def zeros_like_w(w):
+    """Zero gradient buffer for an OIHW-shaped weight held in channels_last (= OHWI) memory."""
+    o, i, kh, kw = w.shape
+    return zeros_f32(w.numel(), w.device).view(o, kh, kw, i).permute(0, 3, 1, 2)
+
+
 def is_cl(x):
     return x.dim() == 4 and (x.shape[1] == 1 or x.stride(1) == 1) and x.dtype == torch.float32
 
@@ -264,8 +290,8 @@ class _BatchNormFn(torch.autograd.Function):
         need_x, need_w, need_b, need_r = ctx.needs_input_grad[:4]
         dx = cl_empty(n, c, h, w, dev) if need_x else None
         dres = cl_empty(n, c, h, w, dev) if (has_res and need_r) else None
-        dgamma = torch.zeros(c, device=dev, dtype=torch.float32) if need_w else None
-        dbeta = torch.zeros(c, device=dev, dtype=torch.float32) if need_b else None
+        dgamma = zeros_f32(c, dev) if need_w else None
+        dbeta = zeros_f32(c, dev) if need_b else None
         A.call("segsde_bn_bwd_apply", C.byref(view(x)), _ref(vy), C.byref(view(dy)), A.ptr(mean), A.ptr(invstd),
                A.ptr(gw), C.c_int(act), C.c_int(1 if training else 0), A.ptr(red), C.c_int64(n * h * w),
                _ref(view(dx)) if dx is not None else None, _ref(view(dres)) if dres is not None else None,
