@@ -305,8 +305,9 @@ def run_b200(args):
     roof_hbm = {"kernel": "reproj_kernel<GRAD> (4 launches per step, one per scale)", "bound": "hbm",
                 "achieved": r_bytes / (r_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": r_bytes / (r_ms * 1e-3) / 1e9 / hbm_peak, "ms_per_step": r_ms / args.steps,
-                "traffic": 273.3e6, "traffic_source": "ncu --set full, scale-0 launch, B=12: dram read 265.5 MB + write 11.9 MB "
-                                                      "(profiles/r1_hot_kernels.md); instruction-bound, not HBM-bound"}
+                "traffic": 344.5e6, "traffic_source": "ncu --set full, scale-0 launch, B=12: dram read 276.9 MB + write 67.6 MB "
+                                                      "incl. the 50 MB identity-candidate cache written once per step "
+                                                      "(profiles/r1_hot_kernels_final.md); instruction-bound, not HBM-bound"}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         import torch as _t
