@@ -299,8 +299,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    // (splitting the activation / weight copies over two issuing warps was measured and does not help here: the
-    // fprop kernels are bound by L2 -> SM bandwidth, not by the issue rate of the bulk copies, unlike wgrad)
+    // (splitting the activation / weight copies over two issuing warps was measured and does not help here: this
+    // kernel is bound by the latency of its operand stream - 160 KB in flight, a stage completing every ~800 clocks,
+    // profiles/r1_generic_kernel.md - not by the issue rate of the bulk copies, unlike wgrad)
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
