@@ -184,6 +184,9 @@ def main():
         f.write("# Oracle vs unmodified reference (%s)\n\n" % REF)
         f.write("torch %s, CPU fp32. Generated by oracle/validate_against_reference.py.\n\n```\n" % torch.__version__)
         f.write("\n".join(report) + "\n```\n\nRESULT: %s\n" % ("ALL OK" if ok else "FAILURES"))
+        f.write("\nThe joint segmentation decoders (JointSegDepthDecoder, PAD) and cross_entropy2d variants are pinned through "
+                "the committed reference outputs instead: tests/golden/make_golden.py runs the unmodified reference on "
+                "seeded inputs, tests/test_oracle_golden.py replays them against this oracle (CPU, any machine).\n")
     sys.exit(0 if ok else 1)
 
 
