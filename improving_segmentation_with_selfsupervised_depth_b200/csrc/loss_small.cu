@@ -267,3 +267,139 @@ extern "C" int segsde_ce_bwd(const segsde_nhwc_t* logits, const int64_t* target,
       lg, (const long long*)target, pixel_w, ignore_index, nullptr, gscale_dev, dl);
   return launched();
 }
+
+// ------------------------------------------------------------------------------------------------
+// berHu pseudo-depth loss (loss/loss.py:5-15, called at train.py:494) and per-pixel normalised entropy
+// (loss/loss.py:40-47, label_selection.py:449).
+// ------------------------------------------------------------------------------------------------
+namespace segsde {
+
+__device__ __forceinline__ float berhu_absdiff(float x, float t, float m, int apply_log, float* sgn, float* dlog) {
+  float dl = 1.f;
+  if (apply_log) { dl = 1.f / (1.f + x); x = logf(1.f + x); t = logf(1.f + t); }
+  const float d = t - x;
+  if (sgn) *sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+  if (dlog) *dlog = dl;
+  return fabsf(d) * m;
+}
+
+// pass 1: max |t - x| * m  (non-negative floats order like their bit patterns -> atomicMax on the bits)
+__global__ void __launch_bounds__(256) berhu_max_kernel(const float* __restrict__ x, const float* __restrict__ t,
+                                                        const float* __restrict__ m, long long n, int apply_log,
+                                                        unsigned int* __restrict__ maxbits) {
+  float best = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    best = fmaxf(best, berhu_absdiff(x[i], t[i], m ? m[i] : 1.f, apply_log, nullptr, nullptr));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+  if ((threadIdx.x & 31) == 0 && best > 0.f) atomicMax(maxbits, __float_as_uint(best));
+}
+
+// pass 2: sum of (a <= C ? a : (a^2 + C^2) / (2C)), C = thr * max — the threshold is read from device memory,
+// the reference's .item() round trip (loss.py:11) is not needed
+__global__ void __launch_bounds__(256) berhu_sum_kernel(const float* __restrict__ x, const float* __restrict__ t,
+                                                        const float* __restrict__ m, long long n, int apply_log,
+                                                        const unsigned int* __restrict__ maxbits, float thr,
+                                                        double* __restrict__ sum) {
+  const float C = thr * __uint_as_float(*maxbits);
+  double acc = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float a = berhu_absdiff(x[i], t[i], m ? m[i] : 1.f, apply_log, nullptr, nullptr);
+    acc += (double)(a <= C ? a : (a * a + C * C) / (2.f * C));
+  }
+  acc = warp_sum_d(acc);
+  __shared__ double red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < 8; ++i) s += red[i];
+    atomicAdd(sum, s);
+  }
+}
+__global__ void berhu_finalize_kernel(const double* __restrict__ sum, double inv_n, float* __restrict__ loss) {
+  loss[0] = (float)(sum[0] * inv_n);
+}
+// d loss / d x = gloss / n * (a <= C ? 1 : a / C) * d a / d x,  d a / d x = -sign(t' - x') * m * (1 / (1 + x) with log)
+__global__ void __launch_bounds__(256) berhu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ t,
+                                                        const float* __restrict__ m, long long n, int apply_log,
+                                                        const unsigned int* __restrict__ maxbits, float thr,
+                                                        const float* __restrict__ gloss, float inv_n,
+                                                        float* __restrict__ dx) {
+  const float C = thr * __uint_as_float(*maxbits);
+  const float g = gloss[0] * inv_n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float sgn, dl;
+    const float mi = m ? m[i] : 1.f;
+    const float a = berhu_absdiff(x[i], t[i], mi, apply_log, &sgn, &dl);
+    const float w = a <= C ? 1.f : a / C;
+    dx[i] = -g * w * sgn * mi * dl;
+  }
+}
+
+// entropy[n,h,w] = -sum_c p log2(p + 1e-30) / log2(C), p = softmax over the channel axis of NCHW logits
+__global__ void __launch_bounds__(256) entropy_kernel(const float* __restrict__ logits, int N, int C, long long HW,
+                                                      float* __restrict__ out, unsigned int* __restrict__ minmax) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float e = 0.f;
+  const bool valid = i < (long long)N * HW;
+  if (valid) {
+    const long long n = i / HW, p = i % HW;
+    const float* l = logits + n * C * HW + p;
+    float mx = -3.4e38f;
+    for (int c = 0; c < C; ++c) mx = fmaxf(mx, l[c * HW]);
+    float den = 0.f;
+    for (int c = 0; c < C; ++c) den += expf(l[c * HW] - mx);
+    const float inv = 1.f / den;
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) { const float pr = expf(l[c * HW] - mx) * inv; s += pr * log2f(pr + 1e-30f); }
+    e = -s / log2f((float)C);
+    out[i] = e;
+  }
+  if (minmax) {       // entropy >= 0 up to rounding: clamp for the bit-pattern ordering of the atomics
+    float lo = valid ? fmaxf(e, 0.f) : 3.4e38f, hi = valid ? fmaxf(e, 0.f) : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMin(minmax, __float_as_uint(lo)); atomicMax(minmax + 1, __float_as_uint(hi)); }
+  }
+}
+__global__ void entropy_normalize_kernel(float* __restrict__ e, long long n, const unsigned int* __restrict__ minmax) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float lo = __uint_as_float(minmax[0]), hi = __uint_as_float(minmax[1]);
+  e[i] = (e[i] - lo) / (hi - lo);
+}
+
+}  // namespace segsde
+
+extern "C" int segsde_berhu_fwd(const float* input, const float* target, const float* mask, int64_t n, int apply_log,
+                                float threshold, unsigned int* maxbits, double* sum, float* loss, void* stream) {
+  if (!input || !target || !maxbits || !sum || !loss || n < 1) return SEGSDE_E_ARG;
+  cudaStream_t st = as_stream(stream);
+  long long blocks = cdiv(n, 256 * 8); if (blocks > 148 * 8) blocks = 148 * 8; if (blocks < 1) blocks = 1;
+  berhu_max_kernel<<<(unsigned)blocks, 256, 0, st>>>(input, target, mask, n, apply_log, maxbits);
+  berhu_sum_kernel<<<(unsigned)blocks, 256, 0, st>>>(input, target, mask, n, apply_log, maxbits, threshold, sum);
+  berhu_finalize_kernel<<<1, 1, 0, st>>>(sum, 1.0 / (double)n, loss);
+  return launched();
+}
+extern "C" int segsde_berhu_bwd(const float* input, const float* target, const float* mask, int64_t n, int apply_log,
+                                float threshold, const unsigned int* maxbits, const float* gloss, float* dinput,
+                                void* stream) {
+  if (!input || !target || !maxbits || !gloss || !dinput || n < 1) return SEGSDE_E_ARG;
+  long long blocks = cdiv(n, 256 * 8); if (blocks > 148 * 8) blocks = 148 * 8; if (blocks < 1) blocks = 1;
+  berhu_bwd_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(input, target, mask, n, apply_log, maxbits, threshold,
+                                                                    gloss, (float)(1.0 / (double)n), dinput);
+  return launched();
+}
+extern "C" int segsde_pixel_entropy(const float* logits, int n, int c, int h, int w, int normalize, float* entropy,
+                                    unsigned int* minmax, void* stream) {
+  if (!logits || !entropy || n < 1 || c < 2 || h < 1 || w < 1 || (normalize && !minmax)) return SEGSDE_E_ARG;
+  const long long hw = (long long)h * w, total = (long long)n * hw;
+  cudaStream_t st = as_stream(stream);
+  entropy_kernel<<<cdiv(total, 256), 256, 0, st>>>(logits, n, c, hw, entropy, normalize ? minmax : nullptr);
+  if (normalize) entropy_normalize_kernel<<<cdiv(total, 256), 256, 0, st>>>(entropy, total, minmax);
+  return launched();
+}

@@ -336,6 +336,21 @@ int segsde_upsample2x_nearest(const segsde_nhwc_t* x, const segsde_nhwc_t* y, vo
  * (the "mean over valid pixels" division of F.cross_entropy without a host sync). */
 int segsde_ratio(const float* acc, float const_den, float* out, float* inv, void* stream);
 
+/* berHu pseudo-depth loss (loss/loss.py:5-15; train.py:494): a = |target - input| * mask (log(1+.) of both first when
+ * apply_log), C = threshold * max(a), loss = mean(a <= C ? a : (a^2 + C^2) / (2C)).  The maximum stays on the device
+ * (maxbits: its float bit pattern, zero-initialised by the caller; sum: zero-initialised fp64 accumulator) — the
+ * reference's .item() round trip is not needed.  mask may be NULL (all ones).  bwd: dinput = d loss / d input * gloss[0]
+ * with C held constant, as in the reference (its C is a Python float). */
+int segsde_berhu_fwd(const float* input, const float* target, const float* mask, int64_t n, int apply_log,
+                     float threshold, unsigned int* maxbits, double* sum, float* loss, void* stream);
+int segsde_berhu_bwd(const float* input, const float* target, const float* mask, int64_t n, int apply_log,
+                     float threshold, const unsigned int* maxbits, const float* gloss, float* dinput, void* stream);
+/* Per-pixel normalised entropy of the softmax over the channel axis of NCHW logits (loss/loss.py:40-47):
+ * entropy[n,h,w] = -sum_c p log2(p + 1e-30) / log2(C); normalize: (e - min) / (max - min) over the whole tensor
+ * (minmax: two words initialised to {0x7f7fffff, 0} by the caller). */
+int segsde_pixel_entropy(const float* logits, int n, int c, int h, int w, int normalize, float* entropy,
+                         unsigned int* minmax, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -151,6 +151,25 @@ def cross_entropy2d(logits, target, class_weight=None, pixel_weights=None):
     return loss
 
 
+def berhu(pred, target, mask, apply_log=False, threshold=0.2):
+    """loss/loss.py:5-15: reverse Huber on the masked absolute difference; the switch point C = threshold * max is a
+    plain number (no gradient flows through it)."""
+    if apply_log:
+        pred, target = torch.log(1 + pred), torch.log(1 + target)
+    a = (target - pred).abs() * mask
+    C = threshold * float(a.detach().max())
+    return torch.where(a <= C, a, (a * a + C * C) / (2 * C)).mean()
+
+
+def pixel_wise_entropy(logits, normalize=False):
+    """loss/loss.py:40-47: per-pixel entropy of the channel softmax, in units of log2(C)."""
+    p = F.softmax(logits, dim=1)
+    ent = -(p * torch.log2(p + 1e-30)).sum(1) / math.log2(logits.shape[1])
+    if normalize:
+        ent = (ent - ent.min()) / (ent.max() - ent.min())
+    return ent
+
+
 # ------------------------------------------------------------------------------------------------
 # pose geometry
 # ------------------------------------------------------------------------------------------------
