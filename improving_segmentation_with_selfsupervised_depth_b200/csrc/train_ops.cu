@@ -1,0 +1,237 @@
+// The step-level ops of SURVEY.md §8(a) rows T1-T4 that sit either side of the model / loss call in the reference's
+// train.py (they are Trainer methods there, not part of models/ or loss/):
+//   T1  feature-distance loss           torch.dist(enc_feat, imnet_feat, p=2)                 train.py:480-484
+//   T2  DepthMix: per-sample disparity normalisation (train.py:688-692), depth-comparison mix mask
+//       (generate_mix_mask "depthcomp", train.py:585-604) and the mix itself (loader/transformsgpu.py:33-47)
+//   T3  pseudo-label selection          max / argmax of the teacher softmax, ignore where the max is 0, confidence
+//       weight = share of pixels with max >= 0.968                                          train.py:644-651
+//   T4  EMA teacher update              ema = a * ema + (1 - a) * p over all parameters       train.py:346-358
+// All HBM-bound streaming kernels; the reference's host round trips (.item(), Python loops over the batch, ~600 tiny
+// kernels for the EMA) are replaced by device-side scalars and one multi-tensor launch per 48 tensors.
+#include "common.cuh"
+
+namespace segsde {
+
+// total order on floats for atomicMin / atomicMax
+__device__ __forceinline__ unsigned int f2ord(float f) {
+  const unsigned int b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned int k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+__device__ __forceinline__ double block_sum_d(double v) {
+  __shared__ double red[32];
+  v = warp_sum_d(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+  if (threadIdx.x == 0)
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+  return s;      // valid in thread 0
+}
+
+// ---- T1 -------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sqdiff_sum_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                         long long n, double* __restrict__ sum) {
+  double acc = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float d = a[i] - b[i];
+    acc += (double)d * (double)d;
+  }
+  const double s = block_sum_d(acc);
+  if (threadIdx.x == 0) atomicAdd(sum, s);
+}
+__global__ void dist_finalize_kernel(const double* __restrict__ sum, float* __restrict__ out) { out[0] = (float)sqrt(sum[0]); }
+__global__ void __launch_bounds__(256) dist_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n,
+                                                       const float* __restrict__ dist, const float* __restrict__ g,
+                                                       float* __restrict__ da, float* __restrict__ db) {
+  const float d = dist[0];
+  const float s = d > 0.f ? g[0] / d : 0.f;        // subgradient 0 at the origin, as torch's norm backward
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = s * (a[i] - b[i]);
+    if (da) da[i] = v;
+    if (db) db[i] = -v;
+  }
+}
+
+// ---- T2 -------------------------------------------------------------------------------------------------------
+// minmax: [B][2] ordered keys, initialised by the caller to {0xffffffff, 0}
+__global__ void __launch_bounds__(256) sample_minmax_kernel(const float* __restrict__ d, long long hw,
+                                                            unsigned int* __restrict__ minmax) {
+  const int b = blockIdx.y;
+  const float* p = d + (long long)b * hw;
+  unsigned int lo = 0xffffffffu, hi = 0u;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned int k = f2ord(p[i]);
+    lo = min(lo, k); hi = max(hi, k);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) { atomicMin(minmax + 2 * b, lo); atomicMax(minmax + 2 * b + 1, hi); }
+}
+__global__ void __launch_bounds__(256) sample_normalize_kernel(const float* __restrict__ d, float* __restrict__ out,
+                                                               long long hw, const unsigned int* __restrict__ minmax) {
+  const int b = blockIdx.y;
+  const float lo = ord2f(minmax[2 * b]), hi = ord2f(minmax[2 * b + 1]);
+  const float inv = 1.f / (hi - lo);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += (long long)gridDim.x * blockDim.x)
+    out[(long long)b * hw + i] = (fminf(fmaxf(d[(long long)b * hw + i], lo), hi) - lo) * inv;
+}
+// mask[i] = [d_i >= d_other - margin] * [d_i >= ft], other = (i + 1) % B
+__global__ void __launch_bounds__(256) depthcomp_mask_kernel(const float* __restrict__ d, int B, long long hw, float margin,
+                                                             float ft, long long* __restrict__ mask) {
+  const long long total = (long long)B * hw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / hw); const long long p = i - (long long)b * hw;
+    const float own = d[i], other = d[(long long)((b + 1) % B) * hw + p];
+    mask[i] = (own >= other - margin && own >= ft) ? 1 : 0;
+  }
+}
+// out[i,c,p] = m[i,p] * x[i,c,p] + (1 - m[i,p]) * x[(i+1)%B,c,p]; x / out addressed through (sn, sc, sp) element strides
+__global__ void __launch_bounds__(256) mix_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                                  const long long* __restrict__ mask_i, const float* __restrict__ mask_f,
+                                                  int B, int C, long long hw, long long xsn, long long xsc, long long xsp,
+                                                  long long osn, long long osc, long long osp, int c_fastest) {
+  const long long total = (long long)B * C * hw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int b, c; long long p;
+    if (c_fastest) { c = (int)(i % C); const long long q = i / C; p = q % hw; b = (int)(q / hw); }
+    else { p = i % hw; const long long q = i / hw; c = (int)(q % C); b = (int)(q / C); }
+    const float m = mask_i ? (float)mask_i[(long long)b * hw + p] : mask_f[(long long)b * hw + p];
+    const float own = x[b * xsn + c * xsc + p * xsp], oth = x[(long long)((b + 1) % B) * xsn + c * xsc + p * xsp];
+    out[b * osn + c * osc + p * osp] = m * own + (1.f - m) * oth;
+  }
+}
+
+// ---- T3 -------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pseudo_label_kernel(const float* __restrict__ prob, int B, int C, long long hw,
+                                                           long long sn, long long sc, long long sp, float thr,
+                                                           long long ignore, long long* __restrict__ label,
+                                                           float* __restrict__ max_prob,
+                                                           unsigned long long* __restrict__ count) {
+  const long long total = (long long)B * hw;
+  unsigned int mine = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / hw); const long long p = i - (long long)b * hw;
+    const float* q = prob + b * sn + p * sp;
+    float best = q[0]; int bi = 0;
+    for (int c = 1; c < C; ++c) { const float v = q[c * sc]; if (v > best) { best = v; bi = c; } }
+    label[i] = best == 0.f ? ignore : (long long)bi;
+    if (max_prob) max_prob[i] = best;
+    mine += best >= thr ? 1u : 0u;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(count, (unsigned long long)mine);
+}
+__global__ void __launch_bounds__(256) fill_ratio_kernel(const unsigned long long* __restrict__ count, double inv_total,
+                                                         float scale, float* __restrict__ w, long long n) {
+  const float v = scale * (float)((double)count[0] * inv_total);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) w[i] = v;
+}
+
+// ---- T4 -------------------------------------------------------------------------------------------------------
+constexpr int MT_TENSORS = 48, MT_BLOCKS = 320, MT_CHUNK = 65536;
+struct MultiAxpby {
+  float* dst[MT_TENSORS];
+  const float* src[MT_TENSORS];
+  long long numel[MT_TENSORS];
+  unsigned char blk_tensor[MT_BLOCKS];
+  int blk_chunk[MT_BLOCKS];
+};
+// dst = alpha * dst + beta * src over a list of tensors; one CTA per (tensor, 64K-element chunk)
+__global__ void __launch_bounds__(256) multi_axpby_kernel(const __grid_constant__ MultiAxpby t, float alpha, float beta) {
+  const int ti = t.blk_tensor[blockIdx.x];
+  const long long base = (long long)t.blk_chunk[blockIdx.x] * MT_CHUNK;
+  const long long end = min(t.numel[ti], base + MT_CHUNK);
+  float* __restrict__ d = t.dst[ti];
+  const float* __restrict__ s = t.src[ti];
+  for (long long i = base + threadIdx.x; i < end; i += blockDim.x) d[i] = alpha * d[i] + beta * s[i];
+}
+
+static unsigned grid_for(long long n) {
+  long long b = cdiv(n, 256 * 8);
+  if (b > 148 * 8) b = 148 * 8;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+}  // namespace segsde
+using namespace segsde;
+
+extern "C" int segsde_feature_distance_fwd(const float* a, const float* b, int64_t n, double* sum, float* dist, void* stream) {
+  if (!a || !b || !sum || !dist || n < 1) return SEGSDE_E_ARG;
+  cudaStream_t st = as_stream(stream);
+  sqdiff_sum_kernel<<<grid_for(n), 256, 0, st>>>(a, b, n, sum);
+  dist_finalize_kernel<<<1, 1, 0, st>>>(sum, dist);
+  return launched();
+}
+extern "C" int segsde_feature_distance_bwd(const float* a, const float* b, int64_t n, const float* dist, const float* g,
+                                           float* da, float* db, void* stream) {
+  if (!a || !b || !dist || !g || (!da && !db) || n < 1) return SEGSDE_E_ARG;
+  dist_bwd_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(a, b, n, dist, g, da, db);
+  return launched();
+}
+extern "C" int segsde_sample_minmax_normalize(const float* d, int b, int64_t hw, unsigned int* minmax, float* out, void* stream) {
+  if (!d || !minmax || !out || b < 1 || b > 65535 || hw < 1) return SEGSDE_E_ARG;
+  cudaStream_t st = as_stream(stream);
+  long long gx = cdiv(hw, 256 * 8); if (gx > 148 * 4) gx = 148 * 4; if (gx < 1) gx = 1;
+  dim3 grid((unsigned)gx, (unsigned)b);
+  sample_minmax_kernel<<<grid, 256, 0, st>>>(d, hw, minmax);
+  sample_normalize_kernel<<<grid, 256, 0, st>>>(d, out, hw, minmax);
+  return launched();
+}
+extern "C" int segsde_depthcomp_mask(const float* d, int b, int64_t hw, float margin, float foreground_threshold,
+                                     int64_t* mask, void* stream) {
+  if (!d || !mask || b < 1 || hw < 1) return SEGSDE_E_ARG;
+  depthcomp_mask_kernel<<<grid_for((long long)b * hw), 256, 0, as_stream(stream)>>>(d, b, hw, margin, foreground_threshold,
+                                                                                    (long long*)mask);
+  return launched();
+}
+extern "C" int segsde_mix(const float* x, float* out, const int64_t* mask_i64, const float* mask_f32, int b, int c,
+                          int64_t hw, int64_t x_sn, int64_t x_sc, int64_t x_sp, int64_t o_sn, int64_t o_sc, int64_t o_sp,
+                          void* stream) {
+  if (!x || !out || (!mask_i64 && !mask_f32) || b < 1 || c < 1 || hw < 1) return SEGSDE_E_ARG;
+  mix_kernel<<<grid_for((long long)b * c * hw), 256, 0, as_stream(stream)>>>(
+      x, out, (const long long*)mask_i64, mask_f32, b, c, hw, x_sn, x_sc, x_sp, o_sn, o_sc, o_sp, (x_sc == 1 && o_sc == 1) ? 1 : 0);
+  return launched();
+}
+extern "C" int segsde_pseudo_label(const float* prob, int b, int c, int64_t hw, int64_t sn, int64_t sc, int64_t sp,
+                                   float threshold, int64_t ignore_index, int64_t* label, float* max_prob,
+                                   unsigned long long* count, float weight_scale, float* pixel_weight, void* stream) {
+  if (!prob || !label || !count || b < 1 || c < 1 || hw < 1) return SEGSDE_E_ARG;
+  cudaStream_t st = as_stream(stream);
+  const long long total = (long long)b * hw;
+  pseudo_label_kernel<<<grid_for(total), 256, 0, st>>>(prob, b, c, hw, sn, sc, sp, threshold, ignore_index, (long long*)label,
+                                                       max_prob, count);
+  if (pixel_weight) fill_ratio_kernel<<<grid_for(total), 256, 0, st>>>(count, 1.0 / (double)total, weight_scale, pixel_weight, total);
+  return launched();
+}
+extern "C" int segsde_multi_axpby(int ntensors, float* const* dst, const float* const* src, const int64_t* numel, float alpha,
+                                  float beta, void* stream) {
+  if (ntensors < 0 || (ntensors && (!dst || !src || !numel))) return SEGSDE_E_ARG;
+  cudaStream_t st = as_stream(stream);
+  MultiAxpby t;
+  int nt = 0, nb = 0;
+  for (int i = 0; i < ntensors; ++i) {
+    if (numel[i] < 0 || (numel[i] && (!dst[i] || !src[i]))) return SEGSDE_E_ARG;
+    const long long chunks = (numel[i] + MT_CHUNK - 1) / MT_CHUNK;
+    long long done = 0;
+    while (done < chunks) {
+      if (nt == MT_TENSORS || nb == MT_BLOCKS) {       // table full: flush
+        multi_axpby_kernel<<<nb, 256, 0, st>>>(t, alpha, beta);
+        nt = nb = 0;
+      }
+      t.dst[nt] = dst[i]; t.src[nt] = src[i]; t.numel[nt] = numel[i];
+      while (done < chunks && nb < MT_BLOCKS) { t.blk_tensor[nb] = (unsigned char)nt; t.blk_chunk[nb] = (int)done; ++nb; ++done; }
+      ++nt;
+    }
+  }
+  if (nb) multi_axpby_kernel<<<nb, 256, 0, st>>>(t, alpha, beta);
+  return launched();
+}

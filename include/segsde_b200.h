@@ -351,6 +351,37 @@ int segsde_berhu_bwd(const float* input, const float* target, const float* mask,
 int segsde_pixel_entropy(const float* logits, int n, int c, int h, int w, int normalize, float* entropy,
                          unsigned int* minmax, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Step-level ops around the model / loss call (Trainer methods in the reference's train.py)
+ * ------------------------------------------------------------------------------------------- */
+/* T1 feature-distance loss, torch.dist(a, b, p=2) (train.py:480-484): dist = sqrt(sum (a-b)^2); sum: zero-filled fp64
+ * scratch.  bwd: da = g[0] * (a - b) / dist, db = -da (either may be NULL); zero when dist == 0. */
+int segsde_feature_distance_fwd(const float* a, const float* b, int64_t n, double* sum, float* dist, void* stream);
+int segsde_feature_distance_bwd(const float* a, const float* b, int64_t n, const float* dist, const float* g, float* da,
+                                float* db, void* stream);
+/* T2 DepthMix.  sample_minmax_normalize: out[b] = (d[b] - min_b) / (max_b - min_b) per sample (train.py:688-692);
+ * minmax: [B][2] words initialised to {0xffffffff, 0}.  depthcomp_mask (train.py:585-604, pairs (i, (i+1) % B)):
+ * mask[i] = [d_i >= d_other - margin] * [d_i >= foreground_threshold] as int64 0/1.  mix (loader/transformsgpu.py:
+ * 33-47, the mask.shape[0] == data.shape[0] branch): out[i] = m[i] * x[i] + (1 - m[i]) * x[(i+1) % B], mask [B,H*W]
+ * int64 or fp32 broadcast over channels; x / out addressed by element strides (sample, channel, pixel). */
+int segsde_sample_minmax_normalize(const float* d, int b, int64_t hw, unsigned int* minmax, float* out, void* stream);
+int segsde_depthcomp_mask(const float* d, int b, int64_t hw, float margin, float foreground_threshold, int64_t* mask,
+                          void* stream);
+int segsde_mix(const float* x, float* out, const int64_t* mask_i64, const float* mask_f32, int b, int c, int64_t hw,
+               int64_t x_sn, int64_t x_sc, int64_t x_sp, int64_t o_sn, int64_t o_sc, int64_t o_sp, void* stream);
+/* T3 pseudo labels (train.py:644-648): label = argmax_c prob (first maximum), ignore_index where the maximum is 0;
+ * count (zero-filled) += #pixels with max >= threshold; pixel_weight (nullable) = weight_scale * count / (B*H*W) at
+ * every pixel — the confidence weight stays on the device (the reference reads it with .item()).  prob addressed by
+ * element strides (sample, channel, pixel); max_prob nullable. */
+int segsde_pseudo_label(const float* prob, int b, int c, int64_t hw, int64_t sn, int64_t sc, int64_t sp, float threshold,
+                        int64_t ignore_index, int64_t* label, float* max_prob, unsigned long long* count,
+                        float weight_scale, float* pixel_weight, void* stream);
+/* T4 EMA teacher update (train.py:346-358) as a multi-tensor kernel: dst[i] = alpha * dst[i] + beta * src[i] for a
+ * list of dense fp32 tensors (HOST arrays of device pointers / element counts); one launch per 48 tensors / 320 chunks
+ * instead of one per parameter. */
+int segsde_multi_axpby(int ntensors, float* const* dst, const float* const* src, const int64_t* numel, float alpha,
+                       float beta, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -171,6 +171,58 @@ def pixel_wise_entropy(logits, normalize=False):
 
 
 # ------------------------------------------------------------------------------------------------
+# step-level ops of train.py
+# ------------------------------------------------------------------------------------------------
+def feature_distance(a, b):
+    """train.py:482."""
+    return torch.dist(a, b, p=2)
+
+
+def normalize_depths(disp):
+    """train.py:688-692 (the clamp to [min, max] there is the identity)."""
+    d = disp.detach().clone()
+    for j in range(d.shape[0]):
+        lo, hi = d[j].min(), d[j].max()
+        d[j] = (d[j] - lo) / (hi - lo)
+    return d
+
+
+def depthcomp_mix_mask(depths, margin, foreground_threshold):
+    """train.py:585-604 with the pairing (i, (i+1) % B) — for B = 2 the reference's (0,1), (1,0)."""
+    B = depths.shape[0]
+    out = []
+    for i in range(B):
+        own, other = depths[i], depths[(i + 1) % B]
+        m = torch.ge(own, other - margin).long() * torch.ge(own, foreground_threshold).long()
+        out.append(m)
+    return torch.cat(out)
+
+
+def mix(mask, data):
+    """loader/transformsgpu.py:33-47, branch mask.shape[0] == data.shape[0]."""
+    B = data.shape[0]
+    return torch.stack([mask[i] * data[i] + (1 - mask[i]) * data[(i + 1) % B] for i in range(B)])
+
+
+def calc_pseudo_label_loss(teacher_softmax, student_logits, consistency_weight=1.0, ignore_index=250):
+    """train.py:644-651."""
+    max_probs, label = torch.max(teacher_softmax, dim=1)
+    label = label.clone()
+    label[max_probs == 0] = ignore_index
+    w = float((max_probs >= 0.968).sum()) / label.numel()
+    weights = w * torch.ones_like(max_probs)
+    return consistency_weight * cross_entropy2d(student_logits, label, pixel_weights=weights), label
+
+
+def update_ema(ema_params, params, alpha_teacher, iteration):
+    """train.py:346-358 (in place on the list of ema tensors)."""
+    alpha = min(1 - 1 / (iteration + 1), alpha_teacher)
+    for e, p in zip(ema_params, params):
+        e[:] = alpha * e + (1 - alpha) * p
+    return alpha
+
+
+# ------------------------------------------------------------------------------------------------
 # pose geometry
 # ------------------------------------------------------------------------------------------------
 
