@@ -235,3 +235,141 @@ extern "C" int segsde_multi_axpby(int ntensors, float* const* dst, const float* 
   if (nb) multi_axpby_kernel<<<nb, 256, 0, st>>>(t, alpha, beta);
   return launched();
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Optimizer step and gradient-norm clipping as multi-tensor kernels (the reference instantiates
+// torch.optim.Adam / SGD through utils/optimizers.py:7-30 and clips with torch.nn.utils.clip_grad_norm_,
+// train.py:516-524).  Same arithmetic as torch's single-tensor reference implementations.
+// ------------------------------------------------------------------------------------------------------------
+namespace segsde {
+
+constexpr int MO_TENSORS = 36;
+struct MultiOpt {
+  float* p[MO_TENSORS];
+  float* g[MO_TENSORS];        // gradients (read; scaled in place by multi_scale)
+  float* s1[MO_TENSORS];       // Adam exp_avg / SGD momentum buffer (nullable)
+  float* s2[MO_TENSORS];       // Adam exp_avg_sq (nullable)
+  long long numel[MO_TENSORS];
+  unsigned char blk_tensor[MT_BLOCKS];
+  int blk_chunk[MT_BLOCKS];
+};
+struct AdamHyper { float beta1, beta2, eps, weight_decay, step_size, bias_c2_sqrt; };   // step_size = lr / (1 - beta1^t)
+struct SgdHyper { float lr, momentum, dampening, weight_decay; int nesterov, first; };
+
+__global__ void __launch_bounds__(256) multi_adam_kernel(const __grid_constant__ MultiOpt t, AdamHyper h) {
+  const int ti = t.blk_tensor[blockIdx.x];
+  const long long base = (long long)t.blk_chunk[blockIdx.x] * MT_CHUNK, end = min(t.numel[ti], base + MT_CHUNK);
+  float* __restrict__ p = t.p[ti]; const float* __restrict__ g = t.g[ti];
+  float* __restrict__ m = t.s1[ti]; float* __restrict__ v = t.s2[ti];
+  const float step_size = h.step_size;
+  for (long long i = base + threadIdx.x; i < end; i += blockDim.x) {
+    float gi = g[i];
+    const float pi = p[i];
+    if (h.weight_decay != 0.f) gi = fmaf(h.weight_decay, pi, gi);
+    const float mi = m[i] + (gi - m[i]) * (1.f - h.beta1);                 // lerp, as torch's exp_avg.lerp_
+    const float vi = h.beta2 * v[i] + (1.f - h.beta2) * (gi * gi);
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) / h.bias_c2_sqrt + h.eps;
+    p[i] = pi - step_size * (mi / denom);
+  }
+}
+__global__ void __launch_bounds__(256) multi_sgd_kernel(const __grid_constant__ MultiOpt t, SgdHyper h) {
+  const int ti = t.blk_tensor[blockIdx.x];
+  const long long base = (long long)t.blk_chunk[blockIdx.x] * MT_CHUNK, end = min(t.numel[ti], base + MT_CHUNK);
+  float* __restrict__ p = t.p[ti]; const float* __restrict__ g = t.g[ti];
+  float* __restrict__ buf = t.s1[ti];
+  for (long long i = base + threadIdx.x; i < end; i += blockDim.x) {
+    const float pi = p[i];
+    float gi = g[i];
+    if (h.weight_decay != 0.f) gi = fmaf(h.weight_decay, pi, gi);
+    if (h.momentum != 0.f) {
+      const float b = h.first ? gi : h.momentum * buf[i] + (1.f - h.dampening) * gi;
+      buf[i] = b;
+      gi = h.nesterov ? gi + h.momentum * b : b;
+    }
+    p[i] = pi - h.lr * gi;
+  }
+}
+__global__ void __launch_bounds__(256) multi_sqnorm_kernel(const __grid_constant__ MultiOpt t, double* __restrict__ sum) {
+  const int ti = t.blk_tensor[blockIdx.x];
+  const long long base = (long long)t.blk_chunk[blockIdx.x] * MT_CHUNK, end = min(t.numel[ti], base + MT_CHUNK);
+  const float* __restrict__ g = t.g[ti];
+  double acc = 0.0;
+  for (long long i = base + threadIdx.x; i < end; i += blockDim.x) acc += (double)g[i] * (double)g[i];
+  const double s = block_sum_d(acc);
+  if (threadIdx.x == 0) atomicAdd(sum, s);
+}
+// total_norm = sqrt(sum); coef = min(1, max_norm / (total_norm + 1e-6))   (torch.nn.utils.clip_grad_norm_)
+__global__ void clip_coef_kernel(const double* __restrict__ sum, float max_norm, float* __restrict__ total_norm,
+                                 float* __restrict__ coef) {
+  const float n = (float)sqrt(sum[0]);
+  total_norm[0] = n;
+  coef[0] = fminf(1.f, max_norm / (n + 1e-6f));
+}
+__global__ void __launch_bounds__(256) multi_scale_kernel(const __grid_constant__ MultiOpt t, const float* __restrict__ coef) {
+  const int ti = t.blk_tensor[blockIdx.x];
+  const long long base = (long long)t.blk_chunk[blockIdx.x] * MT_CHUNK, end = min(t.numel[ti], base + MT_CHUNK);
+  float* __restrict__ g = t.g[ti];
+  const float c = coef[0];
+  for (long long i = base + threadIdx.x; i < end; i += blockDim.x) g[i] *= c;
+}
+
+// walks the tensor list, filling tables of <= MO_TENSORS tensors / MT_BLOCKS chunks and launching `launch(table, nb)`
+template <class F>
+static int for_each_table(int n, float* const* p, float* const* g, float* const* s1, float* const* s2, const int64_t* numel,
+                          F launch) {
+  MultiOpt t;
+  int nt = 0, nb = 0;
+  for (int i = 0; i < n; ++i) {
+    if (numel[i] < 0) return SEGSDE_E_ARG;
+    const long long chunks = (numel[i] + MT_CHUNK - 1) / MT_CHUNK;
+    long long done = 0;
+    while (done < chunks) {
+      if (nt == MO_TENSORS || nb == MT_BLOCKS) { launch(t, nb); nt = nb = 0; }
+      t.p[nt] = p ? p[i] : nullptr; t.g[nt] = g ? g[i] : nullptr;
+      t.s1[nt] = s1 ? s1[i] : nullptr; t.s2[nt] = s2 ? s2[i] : nullptr; t.numel[nt] = numel[i];
+      while (done < chunks && nb < MT_BLOCKS) { t.blk_tensor[nb] = (unsigned char)nt; t.blk_chunk[nb] = (int)done; ++nb; ++done; }
+      ++nt;
+    }
+  }
+  if (nb) launch(t, nb);
+  return launched();
+}
+
+}  // namespace segsde
+
+extern "C" int segsde_multi_adam(int n, float* const* p, float* const* g, float* const* exp_avg, float* const* exp_avg_sq,
+                                 const int64_t* numel, float lr, float beta1, float beta2, float eps, float weight_decay,
+                                 int64_t step, void* stream) {
+  if (n < 0 || (n && (!p || !g || !exp_avg || !exp_avg_sq || !numel)) || step < 1) return SEGSDE_E_ARG;
+  cudaStream_t st = as_stream(stream);
+  AdamHyper h;
+  h.beta1 = beta1; h.beta2 = beta2; h.eps = eps; h.weight_decay = weight_decay;
+  // bias corrections in double on the host, like torch's Python scalars
+  h.step_size = (float)((double)lr / (1.0 - pow((double)beta1, (double)step)));
+  h.bias_c2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  return for_each_table(n, p, g, exp_avg, exp_avg_sq, numel,
+                        [&](const MultiOpt& t, int nb) { multi_adam_kernel<<<nb, 256, 0, st>>>(t, h); });
+}
+extern "C" int segsde_multi_sgd(int n, float* const* p, float* const* g, float* const* momentum_buf, const int64_t* numel,
+                                float lr, float momentum, float dampening, float weight_decay, int nesterov, int first_step,
+                                void* stream) {
+  if (n < 0 || (n && (!p || !g || !numel)) || (momentum != 0.f && n && !momentum_buf)) return SEGSDE_E_ARG;
+  cudaStream_t st = as_stream(stream);
+  SgdHyper h;
+  h.lr = lr; h.momentum = momentum; h.dampening = dampening; h.weight_decay = weight_decay; h.nesterov = nesterov;
+  h.first = first_step;
+  return for_each_table(n, p, g, momentum_buf, nullptr, numel,
+                        [&](const MultiOpt& t, int nb) { multi_sgd_kernel<<<nb, 256, 0, st>>>(t, h); });
+}
+extern "C" int segsde_multi_clip_grad_norm(int n, float* const* g, const int64_t* numel, float max_norm, double* sum,
+                                           float* total_norm, float* coef, void* stream) {
+  if (n < 0 || (n && (!g || !numel)) || !sum || !total_norm || !coef) return SEGSDE_E_ARG;
+  cudaStream_t st = as_stream(stream);
+  int rc = for_each_table(n, nullptr, g, nullptr, nullptr, numel,
+                          [&](const MultiOpt& t, int nb) { multi_sqnorm_kernel<<<nb, 256, 0, st>>>(t, sum); });
+  if (rc) return rc;
+  clip_coef_kernel<<<1, 1, 0, st>>>(sum, max_norm, total_norm, coef);
+  return for_each_table(n, nullptr, g, nullptr, nullptr, numel,
+                        [&](const MultiOpt& t, int nb) { multi_scale_kernel<<<nb, 256, 0, st>>>(t, coef); });
+}

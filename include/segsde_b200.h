@@ -381,6 +381,22 @@ int segsde_pseudo_label(const float* prob, int b, int c, int64_t hw, int64_t sn,
  * instead of one per parameter. */
 int segsde_multi_axpby(int ntensors, float* const* dst, const float* const* src, const int64_t* numel, float alpha,
                        float beta, void* stream);
+/* Optimizer step and gradient clipping as multi-tensor kernels.  The reference builds
+ * torch.optim.Adam / SGD through utils/optimizers.py:7-30 (train.py:291-295) and clips with
+ * torch.nn.utils.clip_grad_norm_ (train.py:516-524); same arithmetic as torch's single-tensor implementations.
+ * All pointer lists are HOST arrays of device pointers to dense fp32 tensors of numel[i] elements.
+ *   adam: g += wd*p; m = lerp(m, g, 1-b1); v = b2*v + (1-b2)*g*g; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+ *   sgd : g += wd*p; buf = first_step ? g : mom*buf + (1-damp)*g; g = nesterov ? g + mom*buf : buf; p -= lr*g
+ *         (momentum_buf may be NULL when momentum == 0)
+ *   clip: total_norm = sqrt(sum g^2) over all tensors -> total_norm[0]; coef[0] = min(1, max_norm/(total_norm+1e-6));
+ *         g *= coef (sum: zero-filled fp64 scratch) */
+int segsde_multi_adam(int n, float* const* p, float* const* g, float* const* exp_avg, float* const* exp_avg_sq,
+                      const int64_t* numel, float lr, float beta1, float beta2, float eps, float weight_decay,
+                      int64_t step, void* stream);
+int segsde_multi_sgd(int n, float* const* p, float* const* g, float* const* momentum_buf, const int64_t* numel, float lr,
+                     float momentum, float dampening, float weight_decay, int nesterov, int first_step, void* stream);
+int segsde_multi_clip_grad_norm(int n, float* const* g, const int64_t* numel, float max_norm, double* sum,
+                                float* total_norm, float* coef, void* stream);
 
 #ifdef __cplusplus
 }
