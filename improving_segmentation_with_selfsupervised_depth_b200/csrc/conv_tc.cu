@@ -136,11 +136,6 @@ __device__ __forceinline__ float act_tc(float v, int act) {
   if (act == SEGSDE_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
   return v;
 }
-static int tc_dbg() {   // experiments only: bit0 skip epilogue stores, bit1 skip TMEM loads
-  static int m = -1;
-  if (m < 0) { const char* e = getenv("SEGSDE_TC_DBG"); m = e ? atoi(e) : 0; }
-  return m;
-}
 
 // Epilogue of one 32-row x 32-column accumulator chunk owned by one warp: bias + activation in registers, then a
 // transpose through a padded shared-memory tile so that every st.global.v4 instruction of the warp writes four
@@ -412,7 +407,6 @@ struct TcRowP {
   long long total_tiles;
   int row_bytes;                     // (128 + 2*dil) * 128 rounded up to 1024
   int base_off_mode;                 // 1: descriptor base_offset = (addr >> 7) & 7 ; 0: always 0
-  int dbg;
   double* stats;
 };
 
@@ -1055,7 +1049,6 @@ extern "C" int segsde_conv2d_fwd_tc_stats(const segsde_nhwc_t* x1, const segsde_
     r.total_tiles = (long long)r.tiles_w * r.tiles_h * r.N * r.tiles_n;
     r.row_bytes = (((128 + 2 * d->dil) * 128) + 1023) / 1024 * 1024;
     r.base_off_mode = rowhalo_mode() == 1;
-    r.dbg = tc_dbg();
     r.stats = stats;
     if (make_act_map(&a0, v1, 128 + 2 * d->dil, 1, 1) && (!C2 || make_act_map(&a1, v2, 128 + 2 * d->dil, 1, 1)) &&
         make_w_map(&b, w, 9 * r.Ctot, Cout, BN)) {

@@ -1,4 +1,4 @@
-"""Forward-only timing of encoder-type convolutions (B=12) — env SEGSDE_TC_DBG selects epilogue experiments."""
+"""Forward-only timing of encoder-type convolutions (B=12), with and without BatchNorm statistics in the epilogue."""
 import sys, os
 sys.path.insert(0, '/root/repo')
 import torch
@@ -28,7 +28,6 @@ cases = [  # cin, cout, k, stride, dil, h_in, w_in, stats
     (512, 2048, 1, 1, 1, 32, 64, True), (2048, 512, 1, 1, 1, 32, 64, True), (512, 512, 3, 1, 2, 32, 64, True),
     (2048, 256, 3, 1, 12, 32, 64, True), (2048, 256, 1, 1, 1, 32, 64, True),
 ]
-print("SEGSDE_TC_DBG =", os.environ.get("SEGSDE_TC_DBG", "0"))
 tot = 0.0
 with torch.no_grad():
     for cin, cout, k, s, d, h, w, st in cases:
