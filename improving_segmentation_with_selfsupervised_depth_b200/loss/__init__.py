@@ -7,23 +7,28 @@ from .monodepth_loss import MonodepthLoss
 
 logger = logging.getLogger("segsde")
 
+# segmentation loss registry (the name `key2loss` is part of the reference's module surface)
 key2loss = {"cross_entropy": cross_entropy2d}
 
 
 def get_segmentation_loss_function(cfg):
+    """`training.segmentation_loss` is either None (plain cross entropy) or {"name": <key2loss key>, **kwargs bound to
+    the loss}; an unknown name raises NotImplementedError (reference :16-30)."""
     spec = cfg["training"]["segmentation_loss"]
     if spec is None:
         logger.info("Using default cross entropy loss")
         return cross_entropy2d
-    name = spec["name"]
-    params = {k: v for k, v in spec.items() if k != "name"}
-    if name not in key2loss:
+    bound = dict(spec)
+    name = bound.pop("name")
+    fn = key2loss.get(name)
+    if fn is None:
         raise NotImplementedError("Loss {} not implemented".format(name))
-    logger.info("Using {} with {} params".format(name, params))
-    return functools.partial(key2loss[name], **params)
+    logger.info("Using {} with {} params".format(name, bound))
+    return functools.partial(fn, **bound)
 
 
 def get_monodepth_loss(cfg, is_train, batch_size=None):
-    if batch_size is None:
-        batch_size = cfg["training"]["batch_size"]
-    return MonodepthLoss(**cfg["training"]["monodepth_loss"], batch_size=batch_size, is_train=is_train)
+    """MonodepthLoss from `training.monodepth_loss` (reference :32-37); the batch size defaults to the training one."""
+    options = dict(cfg["training"]["monodepth_loss"])
+    options["batch_size"] = cfg["training"]["batch_size"] if batch_size is None else batch_size
+    return MonodepthLoss(is_train=is_train, **options)
