@@ -81,3 +81,53 @@ def test_segmentation_decoder_wiring(golden, contracts, name, monkeypatch):
             assert rel_err(out[("disp", s)], golden[p + "disp%d" % s]) < 2e-4
         loss = (loss + cross_entropy2d(input=out["intermediate_semantics"], target=inputs["lbl"])) / 2
     assert abs(float(loss.detach()) - float(golden[p + "loss"])) < 2e-5 * abs(float(golden[p + "loss"]))
+
+
+def test_eval_mode_and_frozen_backbone(contracts, monkeypatch):
+    """Eval mode normalises with the running statistics (oracle BNMode(False)), `freeze_backbone` only clears
+    requires_grad (joint_segmentation_depth.py:158-179) and the frozen encoder receives no gradient."""
+    E.install(monkeypatch)
+    H, W = 64, 96
+    model = _model(contracts, "mono_r18", {"height": H, "width": W, "crop_h": H, "crop_w": W, "freeze_backbone": True}, seed=4)
+    enc_params = [q for n, q in model.named_parameters() if n.startswith("models.encoder.")]
+    assert enc_params and not any(q.requires_grad for q in enc_params)
+    assert all(q.requires_grad for n, q in model.named_parameters() if n.startswith("models.depth."))
+    inputs = O.synthetic_inputs(2, H, W, seed=9)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    model.eval()
+    with contextlib.redirect_stdout(io.StringIO()):
+        out = model(inputs)
+    ref = O.model_forward(sd, inputs, {"num_layers": 18, "rswd": [False] * 3, "frame_ids": [0, -1, 1]}, O.BNMode(False))
+    for s in range(4):
+        assert rel_err(out[("disp", s)], ref[("disp", s)]) < 2e-4
+    assert rel_err(out[("cam_T_cam", 0, -1)], ref[("cam_T_cam", 0, -1)]) < 1e-4
+    # eval mode must not touch the running statistics
+    after = model.state_dict()
+    assert all(torch.equal(after[k], v) for k, v in sd.items() if "running" in k or "num_batches" in k)
+    model.train()
+    with contextlib.redirect_stdout(io.StringIO()):
+        out = model(inputs)
+    sum(out[("disp", s)].mean() for s in range(4)).backward()
+    assert all(q.grad is None for q in enc_params)
+
+
+def test_depth_decoder_partial_execution(contracts, monkeypatch):
+    """`exec_layer` + injected `x` (how PAD drives its decoders in two halves) compose to the full pass."""
+    E.install(monkeypatch)
+    from improving_segmentation_with_selfsupervised_depth_b200.models.depth_decoder import DepthDecoder
+    torch.manual_seed(0)
+    enc_ch = [16, 32, 64, 128, 128]
+    dec = DepthDecoder(enc_ch, range(4), [64, 96], num_ch_dec=[16, 32, 32, 64, 64], intermediate_aspp=True,
+                       aspp_pooling=True, batch_norm=True).eval()
+    feats = [torch.randn(2, c, 32 >> min(i, 3), 48 >> min(i, 3)) for i, c in enumerate(enc_ch)]   # dilated: f3, f4 share a size
+    full = {k: v.clone() for k, v in dec(feats).items()}
+    top = {k: v.clone() for k, v in dec(feats, exec_layer=[4, 3, 2]).items()}
+    assert set(top) == {("upconv", 4), ("upconv", 3), ("upconv", 2), ("disp", 3), ("disp", 2)}
+    rest = dec(feats, x=top[("upconv", 2)], exec_layer=[1, 0])
+    assert set(rest) == {("upconv", 1), ("upconv", 0), ("disp", 1), ("disp", 0)}
+    for k, v in {**top, **rest}.items():
+        assert torch.allclose(v, full[k], atol=1e-6), k
+    assert full[("upconv", 4)].shape[-2:] == feats[3].shape[-2:]          # no upsampling between equally sized stages
+    assert full[("disp", 0)].shape == (2, 1, 64, 96)
+    dec.enable_disparity = False
+    assert not any(k[0] == "disp" for k in dec(feats))
