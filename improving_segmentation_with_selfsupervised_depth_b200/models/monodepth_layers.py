@@ -1,7 +1,6 @@
 """Layer/geometry API of models/monodepth_layers.py on the sm_100a kernels."""
 import ctypes as C
 
-import numpy as np
 import torch
 from torch import nn
 

@@ -1,6 +1,5 @@
 """ResnetEncoder — drop-in for models/resnet_encoder.py:64-101 on the sm_100a kernels."""
 import numpy as np
-import torch
 from torch import nn
 
 from .. import _cabi as A
