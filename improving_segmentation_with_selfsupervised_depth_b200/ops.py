@@ -616,6 +616,9 @@ def cross_entropy(logits, target, pixel_weights=None, ignore_index=250):
     return _RatioFn.apply(acc, den)
 
 
-# the convolution op proper lives in conv_op.py (tensor-core routing, halo preparation, dgrad-as-fprop);
-# the class above is the generic-only form kept for reference by the tests
-from .conv_op import conv2d  # noqa: E402,F811
+# the convolution op proper lives in conv_op.py (tensor-core routing, halo preparation, dgrad-as-fprop), which itself
+# imports this module: resolved at call time so that either module can be imported first
+def conv2d(x1, weight, bias=None, x2=None, **kwargs):  # noqa: F811
+    """y = act(conv(cat(up?(x1), x2)) + bias) — see conv_op.conv2d for the keywords."""
+    from .conv_op import conv2d as impl
+    return impl(x1, weight, bias, x2, **kwargs)
