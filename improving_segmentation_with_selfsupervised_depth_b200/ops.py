@@ -6,6 +6,7 @@ computes anything with torch: torch only owns memory (caching allocator), stream
 graph.  Every op raises if it is handed a CPU tensor — there is no fallback.
 """
 import ctypes as C
+import threading
 
 import torch
 
@@ -43,44 +44,48 @@ def cl_empty(n, c, h, w, device, zero=False):
     return f((n, h, w, c), device=device, dtype=torch.float32).permute(0, 3, 1, 2)
 
 
-_ZPOOL = {}
-_ZPOOL_CHUNK = 1 << 20      # float64 elements per pool chunk (8 MB)
+class _ZeroPool:
+    """Bump allocator over pre-zeroed chunks: accumulators that kernels fill with atomics (BatchNorm statistics,
+    weight / bias gradients) are carved out of one memset chunk instead of costing a fill kernel each.  Every slice is
+    handed out exactly once; a chunk is released by the caching allocator when its last slice dies.  Requests come
+    from the forward thread and from autograd's backward thread, hence the lock."""
+
+    def __init__(self, dtype, chunk_elems, align_elems):
+        self.dtype, self.chunk, self.align = dtype, chunk_elems, align_elems
+        self.state = {}                       # device -> [chunk tensor, elements used]
+        self.lock = threading.Lock()
+
+    def take(self, n, device):
+        n_al = (n + self.align - 1) // self.align * self.align
+        if n_al > self.chunk // 4:            # large requests get their own allocation
+            return torch.zeros(n, device=device, dtype=self.dtype)
+        with self.lock:
+            st = self.state.get(device)
+            if st is None or st[1] + n_al > self.chunk:
+                st = [torch.zeros(self.chunk, device=device, dtype=self.dtype), 0]
+                self.state[device] = st
+            out = st[0][st[1]:st[1] + n]
+            st[1] += n_al
+        return out
+
+
+_ZPOOL_CHUNK = 1 << 20        # float64 elements per chunk (8 MB)
+_ZPOOL32_CHUNK = 1 << 25      # float32 elements per chunk (128 MB): about one training step's weight gradients
+_POOL64 = _ZeroPool(torch.float64, _ZPOOL_CHUNK, 2)       # 16-byte aligned slices
+_POOL32 = _ZeroPool(torch.float32, _ZPOOL32_CHUNK, 64)    # 256-byte aligned slices
+_ZPOOL, _ZPOOL32 = _POOL64.state, _POOL32.state
 
 
 def zeros_f64(n, device):
-    """Zero-filled float64 accumulator (BatchNorm statistics / reductions) carved out of a pre-zeroed pool chunk:
-    one memset per ~1M elements instead of a fill kernel per layer.  Every slice is handed out exactly once; a
-    chunk is released by the allocator when its last slice dies."""
-    n_al = (n + 1) & ~1
-    if n_al > _ZPOOL_CHUNK // 4:
-        return torch.zeros(n, device=device, dtype=torch.float64)
-    st = _ZPOOL.get(device)
-    if st is None or st[1] + n_al > _ZPOOL_CHUNK:
-        st = [torch.zeros(_ZPOOL_CHUNK, device=device, dtype=torch.float64), 0]
-        _ZPOOL[device] = st
-    out = st[0][st[1]:st[1] + n]
-    st[1] += n_al
-    return out
-
-
-_ZPOOL32 = {}
-_ZPOOL32_CHUNK = 1 << 25    # float32 elements per pool chunk (128 MB): about one training step's weight gradients
+    """Zero-filled float64 accumulator (BatchNorm statistics / reductions) from the pool: one memset per ~1M elements
+    instead of a fill kernel per layer."""
+    return _POOL64.take(n, device)
 
 
 def zeros_f32(n, device):
-    """Zero-filled float32 accumulator (weight / bias / BatchNorm-parameter gradients, which the kernels build with
-    atomics) carved out of a pre-zeroed pool chunk — the ~200 per-layer fill kernels of a training step become
-    one memset.  Slices are 256-byte aligned and handed out once; a chunk is released when its last slice dies."""
-    n_al = (n + 63) & ~63
-    if n_al > _ZPOOL32_CHUNK // 4:
-        return torch.zeros(n, device=device, dtype=torch.float32)
-    st = _ZPOOL32.get(device)
-    if st is None or st[1] + n_al > _ZPOOL32_CHUNK:
-        st = [torch.zeros(_ZPOOL32_CHUNK, device=device, dtype=torch.float32), 0]
-        _ZPOOL32[device] = st
-    out = st[0][st[1]:st[1] + n]
-    st[1] += n_al
-    return out
+    """Zero-filled float32 accumulator (weight / bias / BatchNorm-parameter gradients) from the pool — the ~200
+    per-layer fill kernels of a training step become one memset."""
+    return _POOL32.take(n, device)
 
 
 def zeros_like_w(w):
