@@ -156,96 +156,7 @@ def _conv_out_hw(hc, wc, kh, kw, stride, pad, dil):
             (wc + 2 * pad - dil * (kw - 1) - 1) // stride + 1)
 
 
-class _Conv2dFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x1, x2, weight, bias, stride, pad, dil, pad_mode, up1, act, nchw):
-        A.require_cuda(x1, weight)
-        if nchw:
-            x1 = x1.contiguous()
-            x2 = x2.contiguous() if x2 is not None else None
-        else:
-            x1 = as_cl(x1)
-            x2 = as_cl(x2) if x2 is not None else None
-        w = ohwi(weight.detach())
-        cout, _, kh, kw = w.shape
-        n, _, h1, w1 = x1.shape
-        hc, wc = (h1 * 2, w1 * 2) if up1 else (h1, w1)
-        ho, wo = _conv_out_hw(hc, wc, kh, kw, stride, pad, dil)
-        y = cl_empty(n, cout, ho, wo, x1.device)
-        d = _desc(kh, kw, stride, pad, dil, pad_mode, up1, act, nchw)
-        v1, v2, vy = view(x1), (view(x2) if x2 is not None else None), view(y)
-        if nchw:   # planar image: only the shape fields are meaningful
-            v1.sn = v1.sh = v1.sw = 0
-        b = bias.detach() if bias is not None else None
-        st = A.stream_ptr()
-        flops = 2.0 * n * ho * wo * cout * kh * kw * w.shape[1]
-
-        def launch():
-            if USE_TC and not nchw and A.try_call("segsde_conv2d_fwd_tc", C.byref(v1), _ref(v2), A.ptr(w), A.ptr(b),
-                                                  C.byref(vy), C.byref(d), st):
-                return
-            A.call("segsde_conv2d_fwd", C.byref(v1), _ref(v2), A.ptr(w), A.ptr(b), C.byref(vy), C.byref(d), st)
-        _timed("fprop", flops, launch)
-        ctx.save_for_backward(x1, x2, w, y if act != A.ACT_NONE else None)
-        ctx.cfg = (stride, pad, dil, pad_mode, up1, act, nchw, bias is not None)
-        return y
-
-    @staticmethod
-    def backward(ctx, dy):
-        x1, x2, w, y = ctx.saved_tensors
-        stride, pad, dil, pad_mode, up1, act, nchw, has_bias = ctx.cfg
-        cout, _, kh, kw = w.shape
-        st = A.stream_ptr()
-        dy = as_cl(dy)
-        if act != A.ACT_NONE:
-            dz = cl_empty(*dy.shape, dy.device)
-            A.call("segsde_act_bwd", C.byref(view(y)), C.byref(view(dy)), C.byref(view(dz)), C.c_int(act), st)
-        else:
-            dz = dy
-        d = _desc(kh, kw, stride, pad, dil, pad_mode, up1, A.ACT_NONE, nchw)
-        vdz = view(dz)
-        need1, need2, needw, needb = ctx.needs_input_grad[0], ctx.needs_input_grad[1], \
-            ctx.needs_input_grad[2], ctx.needs_input_grad[3]
-        dx1 = dx2 = dw = db = None
-        if (need1 or need2) and not nchw:
-            folded = pad_mode == A.PAD_REFLECT or up1
-            if need1:
-                dx1 = cl_empty(*x1.shape, x1.device, zero=folded)
-            if need2 and x2 is not None:
-                dx2 = cl_empty(*x2.shape, x2.device, zero=folded)
-            g1 = view(dx1) if dx1 is not None else view(x1, null=True)
-            g2 = (view(dx2) if dx2 is not None else view(x2, null=True)) if x2 is not None else None
-            cneed = (x1.shape[1] if dx1 is not None else 0) + (x2.shape[1] if dx2 is not None else 0)
-            flops = 2.0 * dz.shape[0] * dz.shape[2] * dz.shape[3] * cout * kh * kw * cneed
-
-            def launch_d():
-                if USE_TC and A.try_call("segsde_conv2d_dgrad_tc", C.byref(vdz), A.ptr(w), C.byref(g1), _ref(g2),
-                                         C.byref(d), st):
-                    return
-                A.call("segsde_conv2d_dgrad", C.byref(vdz), A.ptr(w), C.byref(g1), _ref(g2), C.byref(d), st)
-            _timed("dgrad", flops, launch_d)
-        if needw or (needb and has_bias):
-            dw = torch.zeros_like(w)
-            db = torch.zeros(cout, device=w.device, dtype=torch.float32) if has_bias else None
-            v1, v2 = view(x1), (view(x2) if x2 is not None else None)
-            if nchw:
-                v1.sn = v1.sh = v1.sw = 0
-            flops = 2.0 * dz.shape[0] * dz.shape[2] * dz.shape[3] * cout * kh * kw * w.shape[1]
-
-            def launch_w():
-                if USE_TC and not nchw and A.try_call("segsde_conv2d_wgrad_tc", C.byref(v1), _ref(v2), C.byref(vdz),
-                                                      A.ptr(dw), A.ptr(db), C.byref(d), st):
-                    return
-                A.call("segsde_conv2d_wgrad", C.byref(v1), _ref(v2), C.byref(vdz), A.ptr(dw), A.ptr(db),
-                       C.byref(d), st)
-            _timed("wgrad", flops, launch_w)
-        return dx1, dx2, dw, db, None, None, None, None, None, None, None
-
-
-def conv2d(x1, weight, bias=None, x2=None, stride=1, pad=0, dil=1, pad_mode=A.PAD_ZERO, up1=False,
-           act=A.ACT_NONE, nchw_norm_in=False):
-    """y = act(conv(cat(up?(x1), x2)) + bias) — see segsde_conv2d_fwd."""
-    return _Conv2dFn.apply(x1, x2, weight, bias, stride, pad, dil, pad_mode, up1, act, nchw_norm_in)
+# (the convolution autograd op itself lives in conv_op.py; `conv2d` at the end of this module forwards to it)
 
 
 # -------------------------------------------------------------------------------------------------
@@ -623,7 +534,7 @@ def cross_entropy(logits, target, pixel_weights=None, ignore_index=250):
 
 # the convolution op proper lives in conv_op.py (tensor-core routing, halo preparation, dgrad-as-fprop), which itself
 # imports this module: resolved at call time so that either module can be imported first
-def conv2d(x1, weight, bias=None, x2=None, **kwargs):  # noqa: F811
+def conv2d(x1, weight, bias=None, x2=None, **kwargs):
     """y = act(conv(cat(up?(x1), x2)) + bias) — see conv_op.conv2d for the keywords."""
     from .conv_op import conv2d as impl
     return impl(x1, weight, bias, x2, **kwargs)
