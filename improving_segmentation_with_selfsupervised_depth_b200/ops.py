@@ -122,14 +122,6 @@ def view(x, null=False):
     return v
 
 
-def shape_view(n, c, h, w):
-    v = A.NHWC()
-    v.ptr = None
-    v.n, v.h, v.w, v.c = n, h, w, c
-    v.sn, v.sh, v.sw = h * w * c, w * c, c
-    return v
-
-
 def _ref(v):
     return C.byref(v) if v is not None else None
 
