@@ -110,10 +110,28 @@ def ptr(t):
 
 
 def require_cuda(*ts):
+    """Every kernel launches on the CURRENT device and stream: tensors must live there (a model on another GPU of
+    the same process must be driven under `torch.cuda.device(...)`)."""
+    cur = None
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise SegsdeError("segsde_b200 ops run on CUDA tensors only (got a %s tensor); there is "
                               "no CPU fallback" % t.device)
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise SegsdeError("tensor on %s but the current CUDA device is %d: wrap the call in "
+                              "torch.cuda.device(tensor.device)" % (t.device, cur))
+
+
+def default_seed(salt):
+    """Seed of the in-kernel Philox streams (dropout masks, auto-mask tie-break noise) when the caller gives none:
+    derived from torch's global seed (`torch.manual_seed`) and the data-parallel rank, so that seeded runs are
+    reproducible and ranks / runs with different seeds draw different masks."""
+    rank = int(os.environ.get("RANK", "0"))
+    return ((int(torch.initial_seed()) ^ int(salt)) * 0x9E3779B97F4A7C15 + rank * 0xD1B54A32D192ED03) & 0x7FFFFFFFFFFFFFFF
 
 
 def launch_count():

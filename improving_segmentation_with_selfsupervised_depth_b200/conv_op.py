@@ -22,12 +22,6 @@ from . import _cabi as A
 from . import ops
 
 TC_STRIDE2_FPROP = True      # 3x3/s2 forward on the tensor cores via TMA element strides
-# disparity heads: "1" = single-pass CUDA-core kernels (conv_head.cu), default "0" = tensor-core GEMM to nine tap planes
-# + stencil.  Measured at 64->1 @512x1024, B=12: fused fwd / dgrad / wgrad 0.99 / 0.66 / 0.89 ms against
-# 0.61+0.09 / 0.67+0.09 / 0.36 ms for the tap-plane route — the single-pass kernels still issue too many
-# load/store wavefronts per pixel, so they stay an opt-in experiment.
-HEAD_FUSED = os.environ.get("SEGSDE_HEAD_FUSED", "0") == "1"
-
 
 def _tc_enabled():
     return ops.USE_TC and A.lib().segsde_tc_available() == 1
@@ -338,14 +332,6 @@ class _HeadConvFn(torch.autograd.Function):
         reflect = int(pad_mode == A.PAD_REFLECT)
         b = bias.detach() if bias is not None else None
         flops = 2.0 * n * h * wd * 9 * c
-        if HEAD_FUSED:
-            # single-pass CUDA-core kernels (conv_head.cu): the heads are HBM-bound, x is read exactly once
-            desc = "head %d->1 k3 out %dx%d (fused)" % (c, h, wd)
-            ops._timed("fprop", flops, lambda: A.call("segsde_head_fwd_fused", C.byref(ops.view(x)), A.ptr(w), A.ptr(b),
-                                                      C.byref(ops.view(y)), C.c_int(act), C.c_int(reflect), st), desc)
-            ctx.save_for_backward(x, w, None, y if act != A.ACT_NONE else None)
-            ctx.cfg = (reflect, act, bias is not None, desc)
-            return y
         wz = ops.zeros_f32(32 * c, dev)
         A.call("segsde_copy_rows", A.ptr(w), C.c_int(c), A.ptr(wz), C.c_int(c), C.c_int(9), C.c_int(c), st)
         z = ops.cl_empty(n, 32, h, wd, dev)
@@ -375,18 +361,6 @@ class _HeadConvFn(torch.autograd.Function):
         else:
             dz = dy
         dx = dw = None
-        if wz is None:       # fused route
-            flops = 2.0 * n * h * wd * 9 * c
-            vdz = ops.view(dz)
-            if need_x:
-                dx = ops.cl_empty(n, c, h, wd, dev)
-                ops._timed("dgrad", flops, lambda: A.call("segsde_head_dgrad_fused", C.byref(vdz), A.ptr(w),
-                                                          C.byref(ops.view(dx)), C.c_int(reflect), st), desc)
-            if need_w:
-                dw = ops.zeros_like_w(w)
-                ops._timed("wgrad", flops, lambda: A.call("segsde_head_wgrad_fused", C.byref(ops.view(x)), C.byref(vdz),
-                                                          A.ptr(dw), C.c_int(reflect), st), desc)
-            return dx, dw, db, None, None
         if need_x or need_w:
             gcol = ops.cl_empty(n, 32, h, wd, dev)
             A.call("segsde_head_gcol", C.byref(ops.view(dz)), C.byref(ops.view(gcol)), C.c_int(reflect), C.c_int(1), st)

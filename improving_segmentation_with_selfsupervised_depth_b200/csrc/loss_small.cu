@@ -147,10 +147,16 @@ __global__ void ratio_kernel(const float* __restrict__ acc, float const_den, flo
 
 // ---- cross entropy ----------------------------------------------------------------------------
 // One thread per pixel; the C logits of a pixel are contiguous (NHWC view), C is small (19).
+__global__ void nan_flag_kernel(const float* __restrict__ x, long long n, float* __restrict__ flag) {
+  bool bad = false;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    bad |= isnan(x[i]);
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) flag[0] = 1.f;
+}
 template <bool BWD>
 __global__ void ce_kernel(View lg, const long long* __restrict__ target, const float* __restrict__ pw,
                           int ignore_index, float* __restrict__ acc, const float* __restrict__ gscale,
-                          View dl) {
+                          View dl, const float* __restrict__ flags) {
   const long long npix = (long long)lg.n * lg.h * lg.w;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   float nll = 0.f, valid = 0.f;
@@ -160,14 +166,19 @@ __global__ void ce_kernel(View lg, const long long* __restrict__ target, const f
     const int n = (int)(i / ((long long)lg.w * lg.h));
     const float* p = lg.p + lg.off(n, y, x);
     const long long t = target[i];
-    const bool ok = (t != ignore_index);
     const int C = lg.c;
+    // labels outside [0, C) other than ignore_index contribute nothing (torch raises a device assert there; here they
+    // are counted in acc[3] so the host can turn them into an error without an out-of-bounds read)
+    const bool in_range = t >= 0 && t < C;
+    const bool ok = (t != ignore_index) && in_range;
+    if (!BWD && t != ignore_index && !in_range) atomicAdd(acc + 3, 1.f);
     float mx = -3.4e38f;
     for (int c = 0; c < C; ++c) mx = fmaxf(mx, p[c]);
     float se = 0.f;
     for (int c = 0; c < C; ++c) se += expf(p[c] - mx);
     const float lse = mx + logf(se);
-    const float wgt = pw ? pw[i] : 1.f;
+    // NaN anywhere in the pixel weights disables the weighting (reference loss/loss.py:31-32): flags[2] != 0
+    const float wgt = (pw && flags[2] == 0.f) ? pw[i] : 1.f;
     if (!BWD) {
       if (ok) { nll = (lse - p[t]) * wgt; valid = 1.f; }
     } else {
@@ -252,19 +263,27 @@ extern "C" int segsde_ce_fwd(const segsde_nhwc_t* logits, const int64_t* target,
   if (!logits || !logits->ptr || !target || !acc) return SEGSDE_E_ARG;
   View lg = mk(logits), none = mk(nullptr);
   const long long npix = (long long)lg.n * lg.h * lg.w;
+  if (pixel_w) {
+    int blocks = cdiv(npix, 1024);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    nan_flag_kernel<<<blocks, 256, 0, as_stream(stream)>>>(pixel_w, npix, acc + 2);
+    int rc = launched();
+    if (rc != SEGSDE_OK) return rc;
+  }
   ce_kernel<false><<<cdiv(npix, 256), 256, 0, as_stream(stream)>>>(
-      lg, (const long long*)target, pixel_w, ignore_index, acc, nullptr, none);
+      lg, (const long long*)target, pixel_w, ignore_index, acc, nullptr, none, acc);
   return launched();
 }
 extern "C" int segsde_ce_bwd(const segsde_nhwc_t* logits, const int64_t* target, const float* pixel_w,
-                             int ignore_index, const float* gscale_dev, const segsde_nhwc_t* dlogits,
-                             void* stream) {
+                             int ignore_index, const float* gscale_dev, const float* acc,
+                             const segsde_nhwc_t* dlogits, void* stream) {
   if (!logits || !logits->ptr || !target || !gscale_dev || !dlogits || !dlogits->ptr) return SEGSDE_E_ARG;
+  if (pixel_w && !acc) return SEGSDE_E_ARG;
   View lg = mk(logits), dl = mk(dlogits);
   if (!same_shape(lg, dl)) return SEGSDE_E_ARG;
   const long long npix = (long long)lg.n * lg.h * lg.w;
   ce_kernel<true><<<cdiv(npix, 256), 256, 0, as_stream(stream)>>>(
-      lg, (const long long*)target, pixel_w, ignore_index, nullptr, gscale_dev, dl);
+      lg, (const long long*)target, pixel_w, ignore_index, nullptr, gscale_dev, dl, acc);
   return launched();
 }
 

@@ -82,14 +82,21 @@ __global__ void __launch_bounds__(256) sample_normalize_kernel(const float* __re
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += (long long)gridDim.x * blockDim.x)
     out[(long long)b * hw + i] = (fminf(fmaxf(d[(long long)b * hw + i], lo), hi) - lo) * inv;
 }
-// mask[i] = [d_i >= d_other - margin] * [d_i >= ft], other = (i + 1) % B
+// mask[i] = [d_i >= d_other - margin] * [d_i >= ft_i], other = (i + 1) % B; ft_i = ft_dev[i] when given (one threshold per
+// sample, drawn on the device like the reference does), else the host scalar.  compare == 0 drops the first factor
+// (mix-mask mode "depth": a plain per-sample disparity threshold).  Exactly one of mask_i / mask_f is written.
 __global__ void __launch_bounds__(256) depthcomp_mask_kernel(const float* __restrict__ d, int B, long long hw, float margin,
-                                                             float ft, long long* __restrict__ mask) {
+                                                             float ft, const float* __restrict__ ft_dev, int compare,
+                                                             long long* __restrict__ mask_i, float* __restrict__ mask_f) {
   const long long total = (long long)B * hw;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int b = (int)(i / hw); const long long p = i - (long long)b * hw;
-    const float own = d[i], other = d[(long long)((b + 1) % B) * hw + p];
-    mask[i] = (own >= other - margin && own >= ft) ? 1 : 0;
+    const float own = d[i];
+    const float thr = ft_dev ? ft_dev[b] : ft;
+    bool keep = own >= thr;
+    if (compare) keep = keep && own >= d[(long long)((b + 1) % B) * hw + p] - margin;
+    if (mask_i) mask_i[i] = keep ? 1 : 0;
+    else mask_f[i] = keep ? 1.f : 0.f;
   }
 }
 // out[i,c,p] = m[i,p] * x[i,c,p] + (1 - m[i,p]) * x[(i+1)%B,c,p]; x / out addressed through (sn, sc, sp) element strides
@@ -187,10 +194,11 @@ extern "C" int segsde_sample_minmax_normalize(const float* d, int b, int64_t hw,
   return launched();
 }
 extern "C" int segsde_depthcomp_mask(const float* d, int b, int64_t hw, float margin, float foreground_threshold,
-                                     int64_t* mask, void* stream) {
-  if (!d || !mask || b < 1 || hw < 1) return SEGSDE_E_ARG;
-  depthcomp_mask_kernel<<<grid_for((long long)b * hw), 256, 0, as_stream(stream)>>>(d, b, hw, margin, foreground_threshold,
-                                                                                    (long long*)mask);
+                                     const float* threshold_dev, int compare, int64_t* mask_i64, float* mask_f32,
+                                     void* stream) {
+  if (!d || (!mask_i64 == !mask_f32) || b < 1 || hw < 1) return SEGSDE_E_ARG;
+  depthcomp_mask_kernel<<<grid_for((long long)b * hw), 256, 0, as_stream(stream)>>>(
+      d, b, hw, margin, foreground_threshold, threshold_dev, compare, (long long*)mask_i64, mask_f32);
   return launched();
 }
 extern "C" int segsde_mix(const float* x, float* out, const int64_t* mask_i64, const float* mask_f32, int b, int c,

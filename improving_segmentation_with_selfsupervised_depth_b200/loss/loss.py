@@ -9,7 +9,9 @@ from .. import ops
 
 def cross_entropy2d(input, target, class_weight=None, pixel_weights=None):
     """Reference :17-37: ignore_index 250, mean over valid pixels; with pixel_weights the mean runs over
-    all pixels.  NaN pixel weights disable the weighting (reference :31-32)."""
+    all pixels.  A NaN anywhere in the pixel weights disables the weighting (reference :31-32; detected on the
+    device, no host round trip).  Labels outside [0, C) other than 250 contribute nothing and are counted
+    (ops.CHECK_LABELS turns them into an error)."""
     if class_weight is not None:
         raise NotImplementedError("class_weight is unused by every reference config (train.py:503,649)")
     n, c, h, w = input.size()

@@ -129,7 +129,7 @@ class MonodepthLoss:
     def __init__(self, num_scales, frame_ids, height, width, batch_size, min_depth, max_depth,
                  test_min_depth, test_max_depth, disparity_smoothness,
                  no_ssim, avg_reprojection, disable_automasking, crop_h=None, crop_w=None, is_train=True,
-                 materialize_outputs=False, noise="philox", seed=0x5E65DE):
+                 materialize_outputs=False, noise="philox", seed=None):
         self.num_scales = num_scales
         self.scales = list(range(self.num_scales))
         self.height = height if crop_h is None or not is_train else crop_h
@@ -153,7 +153,7 @@ class MonodepthLoss:
         # (monodepth_loss.py:163-164) for seeded parity runs; or set .replay_noise to a list of tensors
         self.noise = noise
         self.replay_noise = None
-        self.seed = seed
+        self.seed = A.default_seed(0x5E65DE) if seed is None else seed
         self._step = 0
         if not self.no_ssim:
             from ..models.monodepth_layers import SSIM

@@ -118,33 +118,37 @@ class PAD(nn.Module):
             params.extend(self.seg_intermediate_head.parameters())
         return params
 
+    # The decoder pair runs as a two-phase schedule around one exchange point (reference :135-184):
+    #   phase A: both U-Net decoders from the bottleneck down to the distillation layer,
+    #   exchange: each branch receives the other's features through a sigmoid gate (SelfAttention),
+    #   phase B: both decoders continue from the exchanged tensors to full resolution.
+    def _schedule(self):
+        split = self.last_layer - self.distillation_layer            # index of the "upconv" stage at the exchange
+        return split, list(range(self.dec_n_upconv, split - 1, -1)), list(range(split - 1, -1, -1))
+
+    def _exchange(self, depth_mid, seg_mid):
+        gated_depth = self.sa_depth(depth_mid)      # depth features offered to the segmentation branch
+        gated_seg = self.sa_seg(seg_mid)            # segmentation features offered to the depth branch
+        return ops.add(depth_mid, gated_seg), ops.add(seg_mid, gated_depth), gated_depth
+
+    def _to_label_size(self, logits, size):
+        small = tuple(int(v) for v in np.array(size) // self.output_stride)
+        return logits if small == size else ops.bilinear(logits, size, align_corners=False)
+
     def forward(self, encoder_features):
-        segmentation_size = tuple(encoder_features[0].shape[2:])
-        last_layer_size = tuple(int(v) for v in np.array(segmentation_size) // self.output_stride)
-        dec_distill_i = self.last_layer - self.distillation_layer
-        mid = ("upconv", dec_distill_i)
-        first_layers = list(range(self.dec_n_upconv, dec_distill_i - 1, -1))
-        second_layers = list(range(dec_distill_i - 1, -1, -1))
-
-        depth_features = self.depth_dec(encoder_features, exec_layer=first_layers)
-        seg_features = self.seg_dec(encoder_features, exec_layer=first_layers)
-        if self.side_output:
-            intermediate_seg = self.seg_intermediate_head[0](seg_features[mid])
-        # cross-task gating (reference :152-159)
-        features_sa_depth = self.sa_depth(depth_features[mid])
-        features_sa_seg = self.sa_seg(seg_features[mid])
-        merged_for_seg = ops.add(seg_features[mid], features_sa_depth)
-        merged_for_depth = ops.add(depth_features[mid], features_sa_seg)
-
-        depth_features.update(self.depth_dec(encoder_features, x=merged_for_depth, exec_layer=second_layers))
-        seg_features = self.seg_dec(encoder_features, x=merged_for_seg, exec_layer=second_layers)
-        final_seg = self.seg_final_head[0](_get_layer(features_sa_depth, seg_features, self.final_layer))
-        if self.side_output and last_layer_size != segmentation_size:
-            intermediate_seg = ops.bilinear(intermediate_seg, segmentation_size, align_corners=False)
-        if last_layer_size != segmentation_size:
-            final_seg = ops.bilinear(final_seg, segmentation_size, align_corners=False)
+        size = tuple(encoder_features[0].shape[2:])
+        split, phase_a, phase_b = self._schedule()
+        key = ("upconv", split)
+        branches = {"depth": self.depth_dec, "seg": self.seg_dec}
+        feats = {name: dec(encoder_features, exec_layer=phase_a) for name, dec in branches.items()}
+        side = self.seg_intermediate_head[0](feats["seg"][key]) if self.side_output else None
+        to_depth, to_seg, gated_depth = self._exchange(feats["depth"][key], feats["seg"][key])
+        out = dict(feats["depth"])
+        out.update(self.depth_dec(encoder_features, x=to_depth, exec_layer=phase_b))
+        seg_tail = self.seg_dec(encoder_features, x=to_seg, exec_layer=phase_b)
+        out["semantics"] = self._to_label_size(
+            self.seg_final_head[0](_get_layer(gated_depth, seg_tail, self.final_layer)), size)
+        if side is not None:
+            out["intermediate_semantics"] = self._to_label_size(side, size)
         PAD.first_iter = False
-        out = {**depth_features, "semantics": final_seg}
-        if self.side_output:
-            out["intermediate_semantics"] = intermediate_seg
         return out

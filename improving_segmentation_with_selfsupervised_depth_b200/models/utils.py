@@ -39,9 +39,23 @@ def get_resnet_backbone(backbone_name, backbone_pretraining="none", replace_stri
             sd = torch.load(path, map_location="cpu")
             if num_input_images > 1:   # reference resnet_encoder.py:57-59
                 sd["conv1.weight"] = torch.cat([sd["conv1.weight"]] * num_input_images, 1) / num_input_images
-            backbone.encoder.load_state_dict(sd, strict=False)
+            # strict except for the classifier, which the encoder drops (avgpool / fc become Identity below)
+            own = backbone.encoder.state_dict()
+            missing = [k for k in own if k not in sd and not k.startswith("fc.")]
+            unexpected = [k for k in sd if k not in own and not k.startswith("fc.")]
+            if missing or unexpected:
+                raise RuntimeError("ImageNet checkpoint %s does not match %s: missing %s, unexpected %s"
+                                   % (path, backbone_name, missing[:4], unexpected[:4]))
+            backbone.encoder.load_state_dict({k: v for k, v in sd.items() if k in own}, strict=False)
+        elif os.environ.get("SEGSDE_ALLOW_RANDOM_IMNET", "0") == "1":
+            print("WARNING: ImageNet weights for %s not found at %s — SEGSDE_ALLOW_RANDOM_IMNET=1: random init "
+                  "(the feature-distance target is then a random network)" % (backbone_name, path))
         else:
-            print("WARNING: ImageNet weights for %s not found at %s (no network) — random init" % (backbone_name, path))
+            # the reference downloads torchvision's ImageNet weights here (resnet_encoder.py:52-60); there is no network,
+            # and silently training against a random `imnet_encoder` would not reproduce the reference
+            raise FileNotFoundError("ImageNet weights for %s not found at %s; place torchvision's %s state_dict there "
+                                    "or set SEGSDE_ALLOW_RANDOM_IMNET=1 to continue with random init"
+                                    % (backbone_name, path, backbone_name))
     elif "mono" in backbone_pretraining:
         print('Load ' + backbone_pretraining + 'weights')
         download_model_if_doesnt_exist(backbone_pretraining)

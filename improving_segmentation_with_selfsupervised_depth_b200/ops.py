@@ -6,6 +6,7 @@ computes anything with torch: torch only owns memory (caching allocator), stream
 graph.  Every op raises if it is handed a CPU tensor — there is no fallback.
 """
 import ctypes as C
+import os
 import threading
 
 import torch
@@ -14,6 +15,9 @@ from . import _cabi as A
 
 # route eligible convolutions to the tcgen05 tensor-core kernels (set False to force the generic path)
 USE_TC = True
+# SEGSDE_CHECK_LABELS=1: cross_entropy raises on labels outside [0, C) that are not the ignore index (torch raises a
+# device assert there); off by default because reading the counter synchronises the device
+CHECK_LABELS = os.environ.get("SEGSDE_CHECK_LABELS", "0") == "1"
 
 
 # when a list, every convolution launch is bracketed by CUDA events: (kind, algorithmic flops, ev0, ev1)
@@ -432,9 +436,12 @@ class _DropoutFn(torch.autograd.Function):
         return dx, None, None, None, None
 
 
-def dropout(x, p, training, channelwise=False, seed=0xD20B007, replay_mask=None):
+def dropout(x, p, training, channelwise=False, seed=None, replay_mask=None):
+    """seed=None: A.default_seed (torch.manual_seed + rank); the per-call counter separates layers and steps."""
     if not training or p <= 0.0:
         return x
+    if seed is None:
+        seed = A.default_seed(0xD20B007)
     return _DropoutFn.apply(x, float(p), channelwise, seed, replay_mask)
 
 
@@ -477,9 +484,15 @@ class _CrossEntropyFn(torch.autograd.Function):
     def forward(ctx, logits, target, pixel_weights, ignore_index):
         logits = as_cl(logits)
         A.require_cuda(target)
+        if target.dtype != torch.int64:        # the kernel reads int64 labels (the loader's dtype)
+            target = target.long()
         target = target.contiguous()
+        if target.numel() != logits.shape[0] * logits.shape[2] * logits.shape[3]:
+            raise ValueError("cross_entropy: target %s does not match logits %s" % (tuple(target.shape), tuple(logits.shape)))
         pw = pixel_weights.detach().contiguous().float() if pixel_weights is not None else None
-        acc = torch.zeros(2, device=logits.device, dtype=torch.float32)
+        if pw is not None and pw.numel() != target.numel():
+            raise ValueError("cross_entropy: pixel_weights %s do not match target %s" % (tuple(pw.shape), tuple(target.shape)))
+        acc = torch.zeros(4, device=logits.device, dtype=torch.float32)
         A.call("segsde_ce_fwd", C.byref(view(logits)), A.ptr(target), A.ptr(pw), C.c_int(ignore_index),
                A.ptr(acc), A.stream_ptr())
         ctx.save_for_backward(logits, target, pw, acc)
@@ -493,7 +506,7 @@ class _CrossEntropyFn(torch.autograd.Function):
         g = gacc.contiguous()
         dl = cl_empty(*logits.shape, logits.device)
         A.call("segsde_ce_bwd", C.byref(view(logits)), A.ptr(target), A.ptr(pw), C.c_int(ctx.ignore_index),
-               A.ptr(g), C.byref(view(dl)), A.stream_ptr())
+               A.ptr(g), A.ptr(acc), C.byref(view(dl)), A.stream_ptr())
         return dl, None, None, None
 
 
@@ -511,7 +524,7 @@ class _RatioFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         (inv,) = ctx.saved_tensors
-        out = torch.zeros(2, device=inv.device, dtype=torch.float32)
+        out = torch.zeros(4, device=inv.device, dtype=torch.float32)
         A.call("segsde_scale_by_dev", A.ptr(inv), A.ptr(g.contiguous()), C.c_float(1.0), None, C.c_float(0.0),
                A.ptr(out), C.c_int(0), C.c_int64(1), A.stream_ptr())
         return out, None
@@ -520,6 +533,9 @@ class _RatioFn(torch.autograd.Function):
 def cross_entropy(logits, target, pixel_weights=None, ignore_index=250):
     """Mean NLL over valid pixels, or mean over all pixels of w*NLL when pixel_weights is given."""
     acc = _CrossEntropyFn.apply(logits, target, pixel_weights, ignore_index)
+    if CHECK_LABELS and float(acc[3]) > 0:          # debug switch: costs a device synchronisation
+        raise ValueError("cross_entropy: %d labels outside [0, %d) that are not ignore_index %d"
+                         % (int(acc[3]), logits.shape[1], ignore_index))
     den = 0.0 if pixel_weights is None else float(target.numel())
     return _RatioFn.apply(acc, den)
 

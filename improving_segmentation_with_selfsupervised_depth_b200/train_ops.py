@@ -61,23 +61,53 @@ def normalize_depths(disp):
     return out
 
 
-def depthcomp_mix_mask(depths, margin, foreground_threshold):
+def depthcomp_mix_mask(depths, margin, foreground_threshold, generator=None):
     """`generate_mix_mask` in "depthcomp" mode (train.py:585-604): sample i keeps the pixels where it is in front of
     sample (i+1) % B (disparity >= other - margin) and above the foreground threshold.  Returns int64 B x H x W.
-    (The reference asserts B == 2 and pairs (0,1), (1,0) — the same pairing.)  A (lower, upper) threshold pair is
-    drawn uniformly like there."""
+    (The reference asserts B == 2 and pairs (0,1), (1,0) — the same pairing.)  For a (lower, upper) threshold pair
+    one threshold PER SAMPLE is drawn on the device generator, sample 0 first, exactly the reference's RNG
+    consumption (`torch.rand(1, device=...)` per image, train.py:594-598)."""
     A.require_cuda(depths)
     d = depths.detach().contiguous().float()
     b = d.shape[0]
     hw = d.numel() // b
+    thr_dev, thr = None, 0.0
     if isinstance(foreground_threshold, (tuple, list)):
         lo, hi = foreground_threshold
         assert hi > lo
-        foreground_threshold = float(torch.rand(1).item() * (hi - lo) + lo)
+        thr_dev = torch.cat([torch.rand(1, device=d.device, generator=generator) * (hi - lo) + lo for _ in range(b)])
+    else:
+        thr = float(foreground_threshold)
     mask = torch.empty((b,) + tuple(d.shape[-2:]), device=d.device, dtype=torch.int64)
-    A.call("segsde_depthcomp_mask", A.ptr(d), C.c_int(b), C.c_int64(hw), C.c_float(margin), C.c_float(foreground_threshold),
-           A.ptr(mask), A.stream_ptr())
+    A.call("segsde_depthcomp_mask", A.ptr(d), C.c_int(b), C.c_int64(hw), C.c_float(margin), C.c_float(thr),
+           A.ptr(thr_dev), C.c_int(1), A.ptr(mask), None, A.stream_ptr())
     return mask
+
+
+def depth_mix_mask(depths, min_depth=0.1, max_depth=0.4, generator=None):
+    """`generate_mix_mask` in "depth" mode (train.py:605-615, loader/transformmasks.py:33-42 with a one-element
+    threshold): mask[i] = [disparity_i >= t_i], t_i ~ U(min_depth, max_depth) drawn per sample on the device.
+    Returns fp32 B x H x W like the reference (`.float()`)."""
+    A.require_cuda(depths)
+    d = depths.detach().contiguous().float()
+    b = d.shape[0]
+    hw = d.numel() // b
+    thr = torch.cat([torch.rand(1, device=d.device, generator=generator) * (max_depth - min_depth) + min_depth
+                     for _ in range(b)])
+    mask = torch.empty((b,) + tuple(d.shape[-2:]), device=d.device, dtype=torch.float32)
+    A.call("segsde_depthcomp_mask", A.ptr(d), C.c_int(b), C.c_int64(hw), C.c_float(0.0), C.c_float(0.0), A.ptr(thr),
+           C.c_int(0), None, A.ptr(mask), A.stream_ptr())
+    return mask
+
+
+def generate_mix_mask(mode, depths, margin=0.03, foreground_threshold=0.0, generator=None):
+    """Dispatch over the depth-based modes of `Trainer.generate_mix_mask` (train.py:566-640).  "class" and
+    "depthhist" need host-side numpy sampling in the reference and are not part of the GPU path."""
+    if mode == "depthcomp":
+        return depthcomp_mix_mask(depths, margin, foreground_threshold, generator)
+    if mode == "depth":
+        return depth_mix_mask(depths, generator=generator)
+    raise NotImplementedError("mix-mask mode %r (device path covers 'depthcomp' and 'depth')" % (mode,))
 
 
 def _mix_one(mask, x):

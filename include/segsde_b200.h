@@ -133,15 +133,6 @@ int segsde_stem_pack_w(float* w, float* wp, int cout, int kh, int kw, int cin, i
 int segsde_head_stencil_fwd(const segsde_nhwc_t* z, const segsde_nhwc_t* y, const float* bias, int act, int reflect,
                             int pad, void* stream);
 int segsde_head_gcol(const segsde_nhwc_t* dy, const segsde_nhwc_t* gcol, int reflect, int pad, void* stream);
-/* The same heads in single-pass CUDA-core kernels that read x / write dx exactly once (the heads are HBM-bound:
- * 18*C flops per 4*C input bytes) — C a multiple of 64, pad 1, w = [9][C] (OHWI with O = 1):
- *   fwd  : y = act(bias + conv3x3(x, w)), tap planes kept in shared memory;
- *   dgrad: dx = conv3x3^T(dz, w) incl. the reflection-padding adjoint (dz = gradient w.r.t. the pre-activation);
- *   wgrad: dw[9][C] += sum_pixels g (x) x  (dw zero-filled or holding a running gradient). */
-int segsde_head_fwd_fused(const segsde_nhwc_t* x, const float* w, const float* bias, const segsde_nhwc_t* y, int act,
-                          int reflect, void* stream);
-int segsde_head_dgrad_fused(const segsde_nhwc_t* dz, const float* w, const segsde_nhwc_t* dx, int reflect, void* stream);
-int segsde_head_wgrad_fused(const segsde_nhwc_t* x, const segsde_nhwc_t* dz, float* dw, int reflect, void* stream);
 /* 1 if this process can run the tensor-core path (driver entry point for tensor maps found). */
 int segsde_tc_available(void);
 
@@ -314,15 +305,19 @@ int segsde_axpby(const float* x, float a, float* y, int accumulate, int64_t n, v
 /* ---------------------------------------------------------------------------------------------
  * Segmentation cross-entropy (loss/loss.py:17-37): ignore_index 250, mean over valid pixels,
  * optional per-pixel weights (mean over all pixels).  logits: NHWC view; target int64 [N,H,W].
- * acc: [2] fp32 zero-filled -> acc[0] = sum of (weighted) NLL, acc[1] = number of valid pixels.
+ * acc: [4] fp32 zero-filled -> acc[0] = sum of (weighted) NLL, acc[1] = number of valid pixels,
+ * acc[2] = 1 when pixel_w contains a NaN (the weighting is then skipped, loss.py:31-32),
+ * acc[3] = number of labels outside [0,C) that are not ignore_index (they contribute nothing; torch
+ * raises a device assert for them).
  * ------------------------------------------------------------------------------------------- */
 int segsde_ce_fwd(const segsde_nhwc_t* logits, const int64_t* target, const float* pixel_w,
                   int ignore_index, float* acc, void* stream);
 /* dlogits = gscale_dev[0] * (softmax - onehot) * w ; gscale is a device scalar so that no host
- * sync is needed to divide by the valid count. */
+ * sync is needed to divide by the valid count.  acc: the forward call's acc (its NaN flag decides
+ * whether pixel_w applies); required when pixel_w is given. */
 int segsde_ce_bwd(const segsde_nhwc_t* logits, const int64_t* target, const float* pixel_w,
-                  int ignore_index, const float* gscale_dev, const segsde_nhwc_t* dlogits,
-                  void* stream);
+                  int ignore_index, const float* gscale_dev, const float* acc,
+                  const segsde_nhwc_t* dlogits, void* stream);
 
 /* Standalone layer forms (models/monodepth_layers.py:145-254), NCHW planar fp32 as in the reference. */
 int segsde_backproject(const float* depth, const float* inv_K, int B, int H, int W, float* out /*[B,4,HW]*/,
@@ -361,12 +356,15 @@ int segsde_feature_distance_bwd(const float* a, const float* b, int64_t n, const
                                 float* db, void* stream);
 /* T2 DepthMix.  sample_minmax_normalize: out[b] = (d[b] - min_b) / (max_b - min_b) per sample (train.py:688-692);
  * minmax: [B][2] words initialised to {0xffffffff, 0}.  depthcomp_mask (train.py:585-604, pairs (i, (i+1) % B)):
- * mask[i] = [d_i >= d_other - margin] * [d_i >= foreground_threshold] as int64 0/1.  mix (loader/transformsgpu.py:
+ * mask[i] = [d_i >= d_other - margin] * [d_i >= foreground_threshold] as int64 0/1 (or fp32 0/1 into mask_f32; exactly
+ * one of the two outputs is given); threshold_dev (nullable): one threshold per sample on the device (the reference
+ * draws `ft` per image, train.py:594-598), overriding the host scalar; compare = 0 drops the comparison with the
+ * other sample (mode "depth", train.py:605-615 + loader/transformmasks.py:33-42).  mix (loader/transformsgpu.py:
  * 33-47, the mask.shape[0] == data.shape[0] branch): out[i] = m[i] * x[i] + (1 - m[i]) * x[(i+1) % B], mask [B,H*W]
  * int64 or fp32 broadcast over channels; x / out addressed by element strides (sample, channel, pixel). */
 int segsde_sample_minmax_normalize(const float* d, int b, int64_t hw, unsigned int* minmax, float* out, void* stream);
-int segsde_depthcomp_mask(const float* d, int b, int64_t hw, float margin, float foreground_threshold, int64_t* mask,
-                          void* stream);
+int segsde_depthcomp_mask(const float* d, int b, int64_t hw, float margin, float foreground_threshold,
+                          const float* threshold_dev, int compare, int64_t* mask_i64, float* mask_f32, void* stream);
 int segsde_mix(const float* x, float* out, const int64_t* mask_i64, const float* mask_f32, int b, int c, int64_t hw,
                int64_t x_sn, int64_t x_sc, int64_t x_sp, int64_t o_sn, int64_t o_sc, int64_t o_sp, void* stream);
 /* T3 pseudo labels (train.py:644-648): label = argmax_c prob (first maximum), ignore_index where the maximum is 0;

@@ -156,12 +156,6 @@ def test_disparity_head_routes(rec, monkeypatch):
     y.backward(torch.ones_like(y))
     n = rec.names()
     assert n[0] == "segsde_act_bwd_bias" and "segsde_head_gcol" in n and n.count("segsde_conv2d_wgrad_tc") == 1
-    rec.clear()
-    monkeypatch.setattr(conv_op, "HEAD_FUSED", True)
-    x2 = cl(2, 64, 16, 32)
-    y = ops.conv2d(x2, w, b, pad=1, pad_mode=A.PAD_REFLECT, act=A.ACT_SIGMOID)
-    y.backward(torch.ones_like(y))
-    assert rec.names() == ["segsde_head_fwd_fused", "segsde_act_bwd_bias", "segsde_head_dgrad_fused", "segsde_head_wgrad_fused"]
 
 
 def test_unsupported_tensor_core_shape_takes_the_generic_kernels(monkeypatch):
