@@ -182,7 +182,8 @@ def run_b200(args):
         model = models.get_model(mono_config("resnet50", H, W, freeze_backbone=True), 19).to(dev).train()
     params = [p for p in model.parameters() if p.requires_grad]
     sync = GradSync(params) if world > 1 else None
-    opt = torch.optim.Adam(params, lr=1e-4, fused=True)
+    from improving_segmentation_with_selfsupervised_depth_b200 import optim as segsde_optim
+    opt = segsde_optim.Adam(params, lr=1e-4)       # multi-tensor Adam of this library (no torch optimizer kernels)
     ml = loss.MonodepthLoss(height=H, width=W, batch_size=B, **MONO_LOSS_KW)
 
     host = {k: v.pin_memory() for k, v in synthetic_inputs(B, H, W, seed=1234 + rank).items()}
@@ -196,7 +197,7 @@ def run_b200(args):
         if sync is not None:
             sync.zero()
         else:
-            opt.zero_grad(set_to_none=True)
+            opt.zero_grad(set_to_none=True)       # gradients come from the zero pools / fresh buffers
         out = model(inputs)
         ml.generate_images_pred(inputs, out)
         total = ml.compute_losses(inputs, out)["loss"]

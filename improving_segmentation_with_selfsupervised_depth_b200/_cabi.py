@@ -28,19 +28,19 @@ class ConvDesc(C.Structure):
 
 
 class ReprojArgs(C.Structure):
-    _fields_ = [("tgt", C.c_void_p), ("src", C.c_void_p * 2), ("disp", C.c_void_p),
-                ("K", C.c_void_p), ("inv_K", C.c_void_p), ("T", C.c_void_p * 2),
-                ("noise", C.c_void_p), ("seed", C.c_uint64), ("offset", C.c_uint64),
-                ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("hs", C.c_int32),
-                ("ws", C.c_int32), ("F", C.c_int32), ("min_depth", C.c_float),
-                ("max_depth", C.c_float), ("flags", C.c_int32),
-                ("loss_partial", C.c_void_p), ("ident_sel", C.c_void_p), ("gdisp", C.c_void_p),
-                ("gT_partial", C.c_void_p), ("ident_cache", C.c_void_p), ("ident_mode", C.c_int32)]
+    _fields_ = [("tgt", C.c_void_p), ("src", C.c_void_p * 2), ("K", C.c_void_p), ("inv_K", C.c_void_p),
+                ("T", C.c_void_p * 2), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("F", C.c_int32),
+                ("S", C.c_int32), ("disp", C.c_void_p * 4), ("hs", C.c_int32 * 4), ("ws", C.c_int32 * 4),
+                ("noise", C.c_void_p * 4), ("seed", C.c_uint64), ("offset", C.c_uint64),
+                ("min_depth", C.c_float), ("max_depth", C.c_float), ("flags", C.c_int32),
+                ("loss_partial", C.c_void_p), ("ident_sel", C.c_void_p * 4), ("gdisp", C.c_void_p * 4),
+                ("gT_partial", C.c_void_p)]
 
 
 ACT_NONE, ACT_RELU, ACT_ELU, ACT_SIGMOID = 0, 1, 2, 3
 PAD_ZERO, PAD_REFLECT = 0, 1
 REPROJ_NO_SSIM, REPROJ_AVG, REPROJ_NO_AUTOMASK = 1, 2, 4
+REPROJ_MAX_SCALES = 4
 E_UNSUPPORTED = -3
 
 _lib = None

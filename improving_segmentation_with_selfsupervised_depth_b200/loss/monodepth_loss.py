@@ -4,8 +4,8 @@ Same constructor kwargs, same methods (`generate_images_pred`, `compute_losses`,
 `generate_depth_test_pred`) and the same `{"loss", "loss/<s>"}` result dict, but the whole
 per-scale chain (bilinear disparity upsample -> depth -> backproject -> project -> grid_sample ->
 SSIM+L1 -> identity auto-mask -> min -> mean, plus the edge-aware smoothness term) runs as fused
-sm_100a kernels behind the C-ABI, and its gradient w.r.t. the disparities and the pose matrices
-is produced in the same pass (see csrc/reproj.cu).
+sm_100a kernels behind the C-ABI — ONE launch covers all scales — and its gradient w.r.t. the
+disparities and the pose matrices is produced in the same pass (see csrc/reproj.cu).
 """
 import ctypes as C
 
@@ -26,52 +26,52 @@ class _MonoLossFn(torch.autograd.Function):
         dev = tgt.device
         st = A.stream_ptr()
         need_grad = any(ctx.needs_input_grad[9:])
+        if S > A.REPROJ_MAX_SCALES:
+            raise A.SegsdeError("MonodepthLoss: at most %d scales per fused launch (got %d)" % (A.REPROJ_MAX_SCALES, S))
         tiles = A.lib().segsde_reproj_tiles(C.c_int(H), C.c_int(W))
         reproj = torch.empty(S, device=dev, dtype=torch.float32)
         sacc = torch.zeros(S, 2 + B, device=dev, dtype=torch.float32)
         out = torch.empty(S + 1, device=dev, dtype=torch.float32)
-        partial = torch.empty(B * tiles, device=dev, dtype=torch.float32)
-        gdisps, gTs = [], None
+        partial = torch.empty(S, B * tiles, device=dev, dtype=torch.float32)
+        gdisps, gTs, gT_partial = [], None, None
         if need_grad:
             gTs = torch.empty(S, F, B, 16, device=dev, dtype=torch.float32)
-            gT_partial = torch.empty(F, B, tiles, 12, device=dev, dtype=torch.float32)
+            gT_partial = torch.empty(S, F, B, tiles, 12, device=dev, dtype=torch.float32)
         flags = (A.REPROJ_NO_SSIM if owner.no_ssim else 0) | (A.REPROJ_AVG if owner.avg_reprojection else 0) \
             | (A.REPROJ_NO_AUTOMASK if owner.disable_automasking else 0)
         Kc, iKc = K.contiguous(), inv_K.contiguous()
         Tc = [t.detach().contiguous() for t in Ts]
         owner._step += 1
-        # identity candidates are scale independent: computed by the scale-0 launch, re-read by the others
-        ident = None
-        if not owner.disable_automasking and not owner.avg_reprojection and S > 1:
-            ident = torch.empty(B, F, H, W, device=dev, dtype=torch.float32)
+        ds = []
         for s in range(S):
             d = disps[s].detach()
-            if not d.is_contiguous():
-                d = d.contiguous()
-            hs, ws = d.shape[-2:]
-            a = A.ReprojArgs()
-            a.tgt = tgt.data_ptr()
-            for f in range(F):
-                a.src[f] = srcs[f].data_ptr()
-                a.T[f] = Tc[f].data_ptr()
-            a.disp, a.K, a.inv_K = d.data_ptr(), Kc.data_ptr(), iKc.data_ptr()
-            a.noise = noises[s].data_ptr() if noises is not None else None
-            a.seed, a.offset = owner.seed, owner._step * 8 + s
-            a.B, a.H, a.W, a.hs, a.ws, a.F = B, H, W, hs, ws, F
-            a.min_depth, a.max_depth, a.flags = owner.min_depth, owner.max_depth, flags
-            a.loss_partial = partial.data_ptr()
-            a.ident_sel = sel_out[s].data_ptr() if sel_out is not None else None
-            if ident is not None:
-                a.ident_cache, a.ident_mode = ident.data_ptr(), (1 if s == 0 else 2)
+            ds.append(d if d.is_contiguous() else d.contiguous())
+        # ---- one launch: every scale's warp + SSIM/L1 + auto-mask + min + mean (+ gradients) -------------------
+        a = A.ReprojArgs()
+        a.tgt = tgt.data_ptr()
+        for f in range(F):
+            a.src[f] = srcs[f].data_ptr()
+            a.T[f] = Tc[f].data_ptr()
+        a.K, a.inv_K = Kc.data_ptr(), iKc.data_ptr()
+        a.B, a.H, a.W, a.F, a.S = B, H, W, F, S
+        a.seed, a.offset = owner.seed, owner._step * 8
+        a.min_depth, a.max_depth, a.flags = owner.min_depth, owner.max_depth, flags
+        a.loss_partial = partial.data_ptr()
+        a.gT_partial = gT_partial.data_ptr() if need_grad else None
+        for s in range(S):
+            a.disp[s], a.hs[s], a.ws[s] = ds[s].data_ptr(), ds[s].shape[-2], ds[s].shape[-1]
+            a.noise[s] = noises[s].data_ptr() if noises is not None else None
+            a.ident_sel[s] = sel_out[s].data_ptr() if sel_out is not None else None
             if need_grad:
-                g = torch.zeros_like(d)
+                g = torch.zeros_like(ds[s])
                 gdisps.append(g)
-                a.gdisp, a.gT_partial = g.data_ptr(), gT_partial.data_ptr()
-            A.call("segsde_reproj_fused", C.byref(a), st)
-            A.call("segsde_reproj_finalize", A.ptr(partial), C.c_int(B * tiles), C.c_int64(B * H * W),
-                   C.c_void_p(reproj.data_ptr() + 4 * s),
-                   A.ptr(gT_partial if need_grad else None), A.ptr(Kc), C.c_int(B), C.c_int(tiles),
-                   C.c_int(F), C.c_void_p(gTs[s].data_ptr() if need_grad else 0), st)
+                a.gdisp[s] = g.data_ptr()
+        A.call("segsde_reproj_fused", C.byref(a), st)
+        A.call("segsde_reproj_finalize", A.ptr(partial), C.c_int(B * tiles), C.c_int64(B * H * W), C.c_int(S),
+               A.ptr(reproj), A.ptr(gT_partial), A.ptr(Kc), C.c_int(B), C.c_int(tiles), C.c_int(F), A.ptr(gTs), st)
+        for s in range(S):
+            d = ds[s]
+            hs, ws = d.shape[-2:]
             # smoothness on the scale's own resolution (monodepth_loss.py:182-186)
             col = colors[s]
             mean = torch.empty(B, device=dev, dtype=torch.float32)

@@ -231,42 +231,42 @@ int segsde_pose_matrix_bwd(const float* jac, const float* dM, int b, float* dvec
  * Monodepth photometric loss (loss/monodepth_loss.py:64-192, models/monodepth_layers.py:18-27,
  * 145-199, 224-254): bilinear disparity upsampling, disp->depth, backproject, project,
  * grid_sample(border, align_corners=True), SSIM(3x3, reflect)+L1, identity auto-mask with
- * tie-break noise, per-pixel min, mean — one fused kernel per scale; optional unit gradients
- * w.r.t. the scale's disparity map and the two pose matrices in the same pass.
+ * tie-break noise, per-pixel min, mean — ONE fused launch for all scales (the target / source frames,
+ * the identity candidates and the target window statistics are shared by the scales); optional unit
+ * gradients w.r.t. every scale's disparity map and the two pose matrices in the same pass.
  * ------------------------------------------------------------------------------------------- */
 #define SEGSDE_REPROJ_NO_SSIM 1
 #define SEGSDE_REPROJ_AVG 2
 #define SEGSDE_REPROJ_NO_AUTOMASK 4
+#define SEGSDE_REPROJ_MAX_SCALES 4
 
 typedef struct {
   const float* tgt;       /* [B,3,H,W] ("color",0,0) */
   const float* src[2];    /* [B,3,H,W] ("color",f,0), f = frame_ids[1:] */
-  const float* disp;      /* [B,1,hs,ws] sigmoid disparity of this scale */
   const float* K;         /* [B,4,4] ("K",0) */
   const float* inv_K;     /* [B,4,4] ("inv_K",0) */
   const float* T[2];      /* [B,4,4] cam_T_cam per source frame */
-  const float* noise;     /* [B,Fi,H,W] tie-break noise already scaled by 1e-5, or NULL = Philox */
-  uint64_t seed, offset;  /* Philox stream when noise == NULL */
-  int32_t B, H, W, hs, ws, F;
+  int32_t B, H, W, F, S;  /* S = number of scales (1..SEGSDE_REPROJ_MAX_SCALES) */
+  const float* disp[SEGSDE_REPROJ_MAX_SCALES];   /* [B,1,hs,ws] sigmoid disparity of scale s */
+  int32_t hs[SEGSDE_REPROJ_MAX_SCALES], ws[SEGSDE_REPROJ_MAX_SCALES];
+  const float* noise[SEGSDE_REPROJ_MAX_SCALES];  /* [B,Fi,H,W] tie-break noise already scaled by 1e-5, or NULL = Philox */
+  uint64_t seed, offset;  /* Philox stream of scale s = (seed, offset + s) when noise[s] == NULL */
   float min_depth, max_depth;
   int32_t flags;          /* SEGSDE_REPROJ_* */
   /* outputs */
-  float* loss_partial;    /* [segsde_reproj_num_partials] per-block sums of min-loss */
-  float* ident_sel;       /* [B,H,W] 1.0 where a reprojection candidate won, or NULL */
-  float* gdisp;           /* [B,1,hs,ws] d(mean min-loss)/d disp, accumulated (zero-filled), or NULL */
-  float* gT_partial;      /* [F][B][tiles][12] per-block d/dP partials (only with gdisp) */
-  /* The identity (auto-mask) candidates do not depend on the scale: with ident_mode 1 the launch stores them
-   * into ident_cache [B,F,H,W]; with ident_mode 2 it reads them back instead of recomputing the two SSIM
-   * windows per pixel.  NULL / 0 = always compute. */
-  float* ident_cache;
-  int32_t ident_mode;
+  float* loss_partial;    /* [S][segsde_reproj_num_partials] per-warp sums of the min-loss */
+  float* ident_sel[SEGSDE_REPROJ_MAX_SCALES];    /* [B,H,W] 1.0 where a reprojection candidate won, or NULL */
+  float* gdisp[SEGSDE_REPROJ_MAX_SCALES];        /* [B,1,hs,ws] d(mean min-loss of scale s)/d disp_s, accumulated
+                                                    (zero-filled); all NULL = forward only */
+  float* gT_partial;      /* [S][F][B][tiles][12] per-warp d/dP partials (only with gdisp) */
 } segsde_reproj_args_t;
 
 int segsde_reproj_num_partials(int B, int H, int W);  /* = B * tiles */
-int segsde_reproj_tiles(int H, int W);
+int segsde_reproj_tiles(int H, int W);                /* warps per sample: column strips x row bands */
 int segsde_reproj_fused(const segsde_reproj_args_t* a, void* stream);
-/* loss = sum(partials)/(B*H*W); gT[f][b] (4x4) = K[:3,:]^T * sum_tiles gP. Deterministic order. */
-int segsde_reproj_finalize(const float* loss_partial, int n_partial, int64_t count, float* loss_out,
+/* loss[s] = sum(partials[s])/(B*H*W); gT[s][f][b] (4x4) = K[:3,:]^T * sum_tiles gP. Deterministic order.
+ * loss_out: [S]; gT: [S][F][B][16]. */
+int segsde_reproj_finalize(const float* loss_partial, int n_partial, int64_t count, int S, float* loss_out,
                            const float* gT_partial, const float* K, int B, int tiles, int F,
                            float* gT, void* stream);
 /* Optional materialisation of the reference's side outputs (monodepth_loss.py:78-98):

@@ -37,7 +37,7 @@ def test_argument_errors_do_not_need_a_gpu():
     assert lib.segsde_reproj_fused(None, None) == -1
     assert lib.segsde_conv2d_fwd(None, None, None, None, None, None, None) == -1
     assert b"invalid argument" in lib.segsde_error_string(-1)
-    assert lib.segsde_reproj_tiles(512, 1024) == 32 * 64
+    assert lib.segsde_reproj_tiles(512, 1024) == 37 * 16      # 28-column strips x 32-row bands
 
 
 def test_product_path_refuses_cpu_tensors():
