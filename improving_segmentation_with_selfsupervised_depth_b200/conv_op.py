@@ -49,10 +49,11 @@ def _fwd(x1, x2, w, b, y, d, kind, flops, desc=None, stats=None):
             if stats is not None and A.try_call("segsde_conv2d_fwd_tc_stats", C.byref(v1), ops._ref(v2), A.ptr(w), A.ptr(b),
                                                 C.byref(vy), C.byref(d), A.ptr(stats[0]), st):
                 stats[1] = True
-                return
+                return ops.log_route(kind, True)
             if A.try_call("segsde_conv2d_fwd_tc", C.byref(v1), ops._ref(v2), A.ptr(w), A.ptr(b), C.byref(vy), C.byref(d), st):
-                return
+                return ops.log_route(kind, True)
         A.call("segsde_conv2d_fwd", C.byref(v1), ops._ref(v2), A.ptr(w), A.ptr(b), C.byref(vy), C.byref(d), st)
+        ops.log_route(kind, False)
     ops._timed(kind, flops, launch, desc)
 
 
@@ -169,6 +170,7 @@ class _Conv2dFn(torch.autograd.Function):
                 ops._timed("dgrad", flops_scale * 2.0 * nz * hz * wz * cout * kh * kw * cneed,
                            lambda: A.call("segsde_conv2d_dgrad", C.byref(ops.view(dz)), A.ptr(w), C.byref(v1),
                                           ops._ref(v2), C.byref(d), st), ctx.desc + " generic")
+                ops.log_route("dgrad", False)
                 if g1 is not None:
                     results[0] = g1
                     if sub2:
@@ -201,11 +203,12 @@ class _Conv2dFn(torch.autograd.Function):
             def launch_w():
                 if dz_s is not None and A.try_call("segsde_conv2d_wgrad_tc", C.byref(v1), ops._ref(v2),
                                                    C.byref(ops.view(dz_s)), A.ptr(dw), None, C.byref(d_s), st):
-                    return
+                    return ops.log_route("wgrad", True)
                 if _tc_enabled() and not nchw and A.try_call("segsde_conv2d_wgrad_tc", C.byref(v1), ops._ref(v2),
                                                              C.byref(vdz), A.ptr(dw), None, C.byref(d), st):
-                    return
+                    return ops.log_route("wgrad", True)
                 A.call("segsde_conv2d_wgrad", C.byref(v1), ops._ref(v2), C.byref(vdz), A.ptr(dw), None, C.byref(d), st)
+                ops.log_route("wgrad", False)
             ops._timed("wgrad", flops_scale * 2.0 * nz * hz * wz * cout * kh * kw * ctot, launch_w, ctx.desc)
         return dx1, dx2, dw, db, None, None, None, None, None, None, None, None
 

@@ -899,6 +899,9 @@ static bool make_w_map(CUtensorMap* m, const float* w, int ktot, int cout, int b
   return r == CUDA_SUCCESS;
 }
 
+// which tensor-core kernel the calling thread launched last (SEGSDE_TC_KERNEL_*): lets tests assert the route
+static thread_local int g_last_tc_kernel = 0;
+
 static int num_sms() {
   static int n = 0;
   if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
@@ -919,6 +922,7 @@ static int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
   }
   long long grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   tc_conv_kernel<BN><<<(int)grid, NT_CONV, smem, st>>>(a0, a1, b, p);
+  g_last_tc_kernel = SEGSDE_TC_KERNEL_CONV;
   return launched();
 }
 template <int BN>
@@ -928,6 +932,7 @@ static int launch_wgrad(const CUtensorMap& x0, const CUtensorMap& x1, const CUte
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(tc_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
   tc_wgrad_kernel<BN><<<p.mtiles * p.ntiles * p.splits, NT, smem, st>>>(x0, x1, x5, dy, p);
+  g_last_tc_kernel = SEGSDE_TC_KERNEL_WGRAD;
   return launched();
 }
 
@@ -945,6 +950,7 @@ static int launch_conv3x3(const CUtensorMap& a0, const CUtensorMap& a1, const CU
   }
   long long grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   tc_conv3x3_kernel<BN, NSTAGE><<<(int)grid, NT_CONV, smem, st>>>(a0, a1, b, p);
+  g_last_tc_kernel = SEGSDE_TC_KERNEL_ROWHALO;
   return launched();
 }
 
@@ -971,6 +977,7 @@ static int launch_wgrad3x3(const CUtensorMap& x0, const CUtensorMap& x1, const C
     attr = smem;
   }
   tc_wgrad3x3_kernel<BN, NSTAGE, MINB><<<p.groups * p.units * p.ntiles * p.splits, NT, smem, st>>>(x0, x1, x0p, x1p, dy, p);
+  g_last_tc_kernel = SEGSDE_TC_KERNEL_WGRAD3X3;
   return launched();
 }
 static int wg3_mode() {     // SEGSDE_TC_WGRAD3: 0 = off, 1 (default) = halo-reuse wgrad for 3x3 / stride 1
@@ -998,6 +1005,7 @@ static int pow2_floor(int v) { int r = 1; while (r * 2 <= v) r *= 2; return r; }
 using namespace segsde;
 
 extern "C" int segsde_tc_available(void) { return tc_init() ? 1 : 0; }
+extern "C" int segsde_tc_last_kernel(void) { return g_last_tc_kernel; }
 
 // y = act(conv(cat(x1, x2), w) + bias), zero padding, stride 1 or 2, any dilation; channel counts multiples
 // of 32 (inputs) / 64 (outputs).  Anything else -> SEGSDE_E_UNSUPPORTED (caller uses the generic path).

@@ -116,6 +116,24 @@ __global__ void __launch_bounds__(256) mix_kernel(const float* __restrict__ x, f
 }
 
 // ---- T3 -------------------------------------------------------------------------------------------------------
+// teacher softmax over the class axis (train.py:667): out[b,c,p] = exp(x - max_c) / sum_c, both tensors addressed by
+// (sample, channel, pixel) element strides so NCHW-planar and channels-last logits need no copy; C <= 64
+__global__ void __launch_bounds__(256) softmax_channels_kernel(const float* __restrict__ x, float* __restrict__ out, int B,
+                                                               int C, long long hw, long long xsn, long long xsc,
+                                                               long long xsp, long long osn, long long osc, long long osp) {
+  const long long total = (long long)B * hw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / hw); const long long p = i - (long long)b * hw;
+    const float* q = x + b * xsn + p * xsp;
+    float* o = out + b * osn + p * osp;
+    float mx = q[0];
+    for (int c = 1; c < C; ++c) mx = fmaxf(mx, q[c * xsc]);
+    float se = 0.f;
+    for (int c = 0; c < C; ++c) se += expf(q[c * xsc] - mx);
+    const float inv = 1.f / se;
+    for (int c = 0; c < C; ++c) o[c * osc] = expf(q[c * xsc] - mx) * inv;
+  }
+}
 __global__ void __launch_bounds__(256) pseudo_label_kernel(const float* __restrict__ prob, int B, int C, long long hw,
                                                            long long sn, long long sc, long long sp, float thr,
                                                            long long ignore, long long* __restrict__ label,
@@ -220,6 +238,13 @@ extern "C" int segsde_pseudo_label(const float* prob, int b, int c, int64_t hw, 
   if (pixel_weight) fill_ratio_kernel<<<grid_for(total), 256, 0, st>>>(count, 1.0 / (double)total, weight_scale, pixel_weight, total);
   return launched();
 }
+extern "C" int segsde_softmax_channels(const float* x, float* out, int b, int c, int64_t hw, int64_t x_sn, int64_t x_sc,
+                                       int64_t x_sp, int64_t o_sn, int64_t o_sc, int64_t o_sp, void* stream) {
+  if (!x || !out || b < 1 || c < 1 || hw < 1) return SEGSDE_E_ARG;
+  softmax_channels_kernel<<<grid_for((long long)b * hw), 256, 0, as_stream(stream)>>>(x, out, b, c, hw, x_sn, x_sc, x_sp,
+                                                                                      o_sn, o_sc, o_sp);
+  return launched();
+}
 extern "C" int segsde_multi_axpby(int ntensors, float* const* dst, const float* const* src, const int64_t* numel, float alpha,
                                   float beta, void* stream) {
   if (ntensors < 0 || (ntensors && (!dst || !src || !numel))) return SEGSDE_E_ARG;
@@ -322,6 +347,40 @@ __global__ void __launch_bounds__(256) multi_scale_kernel(const __grid_constant_
   for (long long i = base + threadIdx.x; i < end; i += blockDim.x) g[i] *= c;
 }
 
+// GradScaler.unscale_ (torch._amp_foreach_non_finite_check_and_unscale_): g *= 1 / scale[0]; found_inf[0] = 1 when any
+// element is not finite (the check runs on the unscaled value, like torch's)
+__global__ void __launch_bounds__(256) multi_unscale_kernel(const __grid_constant__ MultiOpt t, const float* __restrict__ scale,
+                                                            float* __restrict__ found_inf) {
+  const int ti = t.blk_tensor[blockIdx.x];
+  const long long base = (long long)t.blk_chunk[blockIdx.x] * MT_CHUNK, end = min(t.numel[ti], base + MT_CHUNK);
+  float* __restrict__ g = t.g[ti];
+  const float c = 1.f / scale[0];
+  bool bad = false;
+  for (long long i = base + threadIdx.x; i < end; i += blockDim.x) {
+    const float v = g[i];
+    bad |= !isfinite(v);
+    g[i] = (c == 1.f) ? v : v * c;
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) found_inf[0] = 1.f;
+}
+// GradScaler.update (torch._amp_update_scale_): back off on overflow, grow after `interval` clean steps
+__global__ void amp_update_scale_kernel(float* __restrict__ scale, int* __restrict__ tracker, const float* __restrict__ found_inf,
+                                        float growth, float backoff, int interval) {
+  if (found_inf[0] != 0.f) {
+    scale[0] *= backoff;
+    tracker[0] = 0;
+  } else {
+    const int ok = tracker[0] + 1;
+    if (ok == interval) {
+      const float grown = scale[0] * growth;
+      if (isfinite(grown)) scale[0] = grown;
+      tracker[0] = 0;
+    } else {
+      tracker[0] = ok;
+    }
+  }
+}
+
 // walks the tensor list, filling tables of <= MO_TENSORS tensors / MT_BLOCKS chunks and launching `launch(table, nb)`
 template <class F>
 static int for_each_table(int n, float* const* p, float* const* g, float* const* s1, float* const* s2, const int64_t* numel,
@@ -369,6 +428,20 @@ extern "C" int segsde_multi_sgd(int n, float* const* p, float* const* g, float* 
   h.first = first_step;
   return for_each_table(n, p, g, momentum_buf, nullptr, numel,
                         [&](const MultiOpt& t, int nb) { multi_sgd_kernel<<<nb, 256, 0, st>>>(t, h); });
+}
+extern "C" int segsde_multi_unscale(int n, float* const* g, const int64_t* numel, const float* scale, float* found_inf,
+                                    void* stream) {
+  if (n < 0 || (n && (!g || !numel)) || !scale || !found_inf) return SEGSDE_E_ARG;
+  cudaStream_t st = as_stream(stream);
+  return for_each_table(n, nullptr, g, nullptr, nullptr, numel,
+                        [&](const MultiOpt& t, int nb) { multi_unscale_kernel<<<nb, 256, 0, st>>>(t, scale, found_inf); });
+}
+extern "C" int segsde_amp_update_scale(float* scale, int* growth_tracker, const float* found_inf, float growth_factor,
+                                       float backoff_factor, int growth_interval, void* stream) {
+  if (!scale || !growth_tracker || !found_inf || growth_interval < 1) return SEGSDE_E_ARG;
+  amp_update_scale_kernel<<<1, 1, 0, as_stream(stream)>>>(scale, growth_tracker, found_inf, growth_factor, backoff_factor,
+                                                         growth_interval);
+  return launched();
 }
 extern "C" int segsde_multi_clip_grad_norm(int n, float* const* g, const int64_t* numel, float max_norm, double* sum,
                                            float* total_norm, float* coef, void* stream) {

@@ -69,9 +69,35 @@ class BatchNorm2d(nn.BatchNorm2d):
         super()._load_from_state_dict(*args, **kwargs)
 
 
+# eval-mode inference (no autograd): fold BatchNorm's running statistics into the convolution weights so that
+# conv -> BN -> ReLU is ONE convolution with a bias + ReLU epilogue (the reference's validate(),
+# train.py:817-923, runs the same layers as conv + BN + ReLU kernels)
+FOLD_EVAL_BN = os.environ.get("SEGSDE_FOLD_EVAL_BN", "1") != "0"
+
+
+def fold_bn(conv, bn):
+    """(w', b') with BatchNorm's eval-mode affine map folded into the convolution (segsde_bn_fold)."""
+    import ctypes as C
+    w = ops.ohwi(conv.weight.detach())
+    cout = w.shape[0]
+    wf = torch.empty_like(w)
+    bf = torch.empty(cout, device=w.device, dtype=torch.float32)
+    A.call("segsde_bn_fold", A.ptr(w), A.ptr(conv.bias.detach() if conv.bias is not None else None),
+           A.ptr(bn.weight.detach() if bn.weight is not None else None),
+           A.ptr(bn.bias.detach() if bn.bias is not None else None), A.ptr(bn.running_mean), A.ptr(bn.running_var),
+           C.c_float(bn.eps), C.c_int(cout), C.c_int(w.numel() // cout), A.ptr(wf), A.ptr(bf), A.stream_ptr())
+    return wf, bf
+
+
 def conv_bn(conv, bn, x, residual=None, act=A.ACT_NONE, **conv_kw):
     """bn(conv(x)) [+ residual] [ReLU] with the BatchNorm batch statistics accumulated in the convolution's
-    tensor-core epilogue (no separate pass over the conv output) when the BN layer normalises with batch statistics."""
+    tensor-core epilogue (no separate pass over the conv output) when the BN layer normalises with batch statistics;
+    in eval-mode inference the BatchNorm is folded into the convolution (no BatchNorm pass at all)."""
+    if (FOLD_EVAL_BN and residual is None and not torch.is_grad_enabled() and isinstance(bn, BatchNorm2d)
+            and isinstance(conv, Conv2d) and not bn.uses_batch_stats() and bn.running_mean is not None
+            and not conv_kw.get("nchw_norm_in", False) and conv.weight.is_cuda):
+        wf, bf = fold_bn(conv, bn)
+        return ops.conv2d(x, wf, bf, stride=conv.stride[0], pad=conv.padding[0], dil=conv.dilation[0], act=act, **conv_kw)
     if (isinstance(bn, BatchNorm2d) and bn.uses_batch_stats() and isinstance(conv, Conv2d) and conv.bias is None
             and os.environ.get("SEGSDE_NO_BNFUSE", "0") != "1"):
         sums = ops.zeros_f64(3 * conv.out_channels, conv.weight.device)
@@ -79,16 +105,23 @@ def conv_bn(conv, bn, x, residual=None, act=A.ACT_NONE, **conv_kw):
     return bn(conv(x, **conv_kw), residual=residual, act=act)
 
 
+def _next_mask(m):
+    """`replay_mask`: None, one NCHW 0/1 tensor (every call), or a list consumed one mask per training-mode call."""
+    if isinstance(m.replay_mask, list):
+        return m.replay_mask.pop(0) if (m.training and m.p > 0 and m.replay_mask) else None
+    return m.replay_mask
+
+
 class Dropout(nn.Dropout):
-    """nn.Dropout on the Philox dropout kernel; `replay_mask` (NCHW 0/1 tensor) pins the mask in tests."""
+    """nn.Dropout on the Philox dropout kernel; `replay_mask` pins the mask(s) in parity tests."""
     replay_mask = None
 
     def forward(self, x):
-        return ops.dropout(x, self.p, self.training, channelwise=False, replay_mask=self.replay_mask)
+        return ops.dropout(x, self.p, self.training, channelwise=False, replay_mask=_next_mask(self))
 
 
 class Dropout2d(nn.Dropout2d):
     replay_mask = None
 
     def forward(self, x):
-        return ops.dropout(x, self.p, self.training, channelwise=True, replay_mask=self.replay_mask)
+        return ops.dropout(x, self.p, self.training, channelwise=True, replay_mask=_next_mask(self))

@@ -25,6 +25,15 @@ PROFILE = None
 
 
 PROFILE_DESC = None   # optional parallel list of human-readable shapes (profiling scripts)
+# when a list, every convolution launch appends (kind, route): route = "tc:<kernel>" (kernel = conv | rowhalo | wgrad |
+# wgrad3x3, the tcgen05 family) or "generic" (CUDA-core fallback for shapes outside the family) — tests assert on it
+ROUTES = None
+_TC_KERNELS = {1: "conv", 2: "rowhalo", 3: "wgrad", 4: "wgrad3x3"}
+
+
+def log_route(kind, tc):
+    if ROUTES is not None:
+        ROUTES.append((kind, "tc:" + _TC_KERNELS.get(A.lib().segsde_tc_last_kernel(), "?") if tc else "generic"))
 
 
 def _timed(kind, flops, fn, desc=None):

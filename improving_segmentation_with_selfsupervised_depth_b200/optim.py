@@ -149,3 +149,97 @@ def clip_grad_norm_(parameters, max_norm, norm_type=2.0):
     A.call("segsde_multi_clip_grad_norm", C.c_int(n), _ptr_array(grads), numel, C.c_float(max_norm),
            A.ptr(ops.zeros_f64(1, dev)), A.ptr(total), A.ptr(coef), A.stream_ptr())
     return total
+
+
+class GradScaler:
+    """`torch.cuda.amp.GradScaler` for the calls the reference makes (train.py:336, 486-530): `scale(loss)`,
+    `unscale_(optimizer)`, `step(optimizer)`, `update()`, plus `get_scale` / `state_dict` / `load_state_dict`.  The
+    scale, the growth tracker and the found-inf flag live on the device; unscaling + the inf check of ALL gradients is
+    one multi-tensor launch per 36 tensors.  `step` reads the flag back once (as torch's does) to decide whether to
+    skip the optimizer.  The convolutions of this library compute in TF32 with fp32 storage under any autocast state
+    (the custom Functions take fp32 inputs), so with `enabled=True` the scaler guards only against overflow of the
+    scaled loss — it exists so that a `train.py` written for AMP runs unchanged."""
+
+    def __init__(self, init_scale=2.0 ** 16, growth_factor=2.0, backoff_factor=0.5, growth_interval=2000, enabled=True):
+        self._enabled = bool(enabled)
+        self._init_scale, self._growth_factor = float(init_scale), float(growth_factor)
+        self._backoff_factor, self._growth_interval = float(backoff_factor), int(growth_interval)
+        self._scale = self._tracker = self._found = None
+        self._unscaled = set()
+
+    def is_enabled(self):
+        return self._enabled
+
+    def _lazy(self, dev):
+        if self._scale is None:
+            self._scale = torch.full((1,), self._init_scale, device=dev, dtype=torch.float32)
+            self._tracker = torch.zeros(1, device=dev, dtype=torch.int32)
+            self._found = torch.zeros(1, device=dev, dtype=torch.float32)
+
+    def scale(self, outputs):
+        if not self._enabled:
+            return outputs
+        A.require_cuda(outputs)
+        self._lazy(outputs.device)
+        return outputs * self._scale.squeeze(0)
+
+    def unscale_(self, optimizer):
+        if not self._enabled:
+            return
+        if id(optimizer) in self._unscaled:
+            raise RuntimeError("unscale_() has already been called on this optimizer since the last update().")
+        grads = [p.grad for g in optimizer.param_groups for p in g["params"] if p.grad is not None]
+        if grads:
+            for g in grads:
+                A.require_cuda(g)
+                if g.dtype != torch.float32 or not _dense(g):
+                    raise NotImplementedError("GradScaler.unscale_: dense fp32 CUDA gradients")
+            self._lazy(grads[0].device)
+            n = len(grads)
+            numel = (C.c_int64 * n)(*[g.numel() for g in grads])
+            A.call("segsde_multi_unscale", C.c_int(n), _ptr_array(grads), numel, A.ptr(self._scale), A.ptr(self._found),
+                   A.stream_ptr())
+        self._unscaled.add(id(optimizer))
+
+    def step(self, optimizer, *args, **kwargs):
+        if not self._enabled:
+            return optimizer.step(*args, **kwargs)
+        if id(optimizer) not in self._unscaled:
+            self.unscale_(optimizer)
+        if self._found is not None and float(self._found) != 0.0:      # one read-back per step, like torch's GradScaler
+            return None
+        return optimizer.step(*args, **kwargs)
+
+    def update(self, new_scale=None):
+        if not self._enabled or self._scale is None:
+            return
+        if new_scale is not None:
+            self._scale.fill_(float(new_scale))
+        else:
+            A.call("segsde_amp_update_scale", A.ptr(self._scale), A.ptr(self._tracker), A.ptr(self._found),
+                   C.c_float(self._growth_factor), C.c_float(self._backoff_factor), C.c_int(self._growth_interval),
+                   A.stream_ptr())
+        self._found.zero_()
+        self._unscaled.clear()
+
+    def get_scale(self):
+        if not self._enabled:
+            return 1.0
+        return self._init_scale if self._scale is None else float(self._scale)
+
+    def state_dict(self):
+        if not self._enabled:
+            return {}
+        return {"scale": self.get_scale(), "growth_factor": self._growth_factor, "backoff_factor": self._backoff_factor,
+                "growth_interval": self._growth_interval,
+                "_growth_tracker": 0 if self._tracker is None else int(self._tracker)}
+
+    def load_state_dict(self, state):
+        if not self._enabled:
+            return
+        self._init_scale = float(state["scale"])
+        self._growth_factor, self._backoff_factor = float(state["growth_factor"]), float(state["backoff_factor"])
+        self._growth_interval = int(state["growth_interval"])
+        if self._scale is not None:
+            self._scale.fill_(self._init_scale)
+            self._tracker.fill_(int(state["_growth_tracker"]))

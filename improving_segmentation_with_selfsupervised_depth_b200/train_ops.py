@@ -140,6 +140,23 @@ def mix(mask, data=None, target=None):
 
 
 # ---- T3 --------------------------------------------------------------------------------------------------------
+def softmax_channels(logits):
+    """`torch.softmax(logits.detach(), dim=1)` of train.py:667 (teacher probabilities; no gradient).  The result keeps
+    the memory format of the input."""
+    A.require_cuda(logits)
+    x = logits.detach().float()
+    if x.dim() != 4:
+        raise ValueError("softmax_channels: B x C x H x W logits expected")
+    if not (x.is_contiguous() or x.is_contiguous(memory_format=torch.channels_last)):
+        x = x.contiguous()
+    b, c, h, w = x.shape
+    out = torch.empty_like(x)
+    A.call("segsde_softmax_channels", A.ptr(x), A.ptr(out), C.c_int(b), C.c_int(c), C.c_int64(h * w), C.c_int64(x.stride(0)),
+           C.c_int64(x.stride(1)), C.c_int64(x.stride(3)), C.c_int64(out.stride(0)), C.c_int64(out.stride(1)),
+           C.c_int64(out.stride(3)), A.stream_ptr())
+    return out
+
+
 def pseudo_labels(teacher_softmax, threshold=0.968, ignore_index=250, weight_scale=1.0):
     """train.py:645-648: (pseudo_label int64 B x H x W, pixel weights fp32 B x H x W) — the label is the arg-max
     class (ignore_index where the maximum is exactly 0), every pixel weight is weight_scale * share of pixels whose

@@ -135,6 +135,13 @@ int segsde_head_stencil_fwd(const segsde_nhwc_t* z, const segsde_nhwc_t* y, cons
 int segsde_head_gcol(const segsde_nhwc_t* dy, const segsde_nhwc_t* gcol, int reflect, int pad, void* stream);
 /* 1 if this process can run the tensor-core path (driver entry point for tensor maps found). */
 int segsde_tc_available(void);
+/* The tensor-core kernel the calling thread launched last (0 = none yet) — test / profiling aid: which member of the
+ * family a shape was routed to. */
+#define SEGSDE_TC_KERNEL_CONV 1      /* tc_conv_kernel: one TMA box per tap (1x1, strided, narrow layers) */
+#define SEGSDE_TC_KERNEL_ROWHALO 2   /* tc_conv3x3_kernel: 3x3 / stride 1, >= 128 px wide, row-halo reuse */
+#define SEGSDE_TC_KERNEL_WGRAD 3     /* tc_wgrad_kernel */
+#define SEGSDE_TC_KERNEL_WGRAD3X3 4  /* tc_wgrad3x3_kernel: halo-reuse weight gradient */
+int segsde_tc_last_kernel(void);
 
 /* y = act(x) as a standalone pass (ConvBlock with BatchNorm: conv -> BN -> ELU). */
 int segsde_act_fwd(const segsde_nhwc_t* x, const segsde_nhwc_t* y, int act, void* stream);
@@ -367,6 +374,10 @@ int segsde_depthcomp_mask(const float* d, int b, int64_t hw, float margin, float
                           const float* threshold_dev, int compare, int64_t* mask_i64, float* mask_f32, void* stream);
 int segsde_mix(const float* x, float* out, const int64_t* mask_i64, const float* mask_f32, int b, int c, int64_t hw,
                int64_t x_sn, int64_t x_sc, int64_t x_sp, int64_t o_sn, int64_t o_sc, int64_t o_sp, void* stream);
+/* Teacher softmax over the class axis (train.py:667, `torch.softmax(logits_u_w.detach(), dim=1)`): x / out addressed by
+ * (sample, channel, pixel) element strides, so planar and channels-last tensors both work without a copy. */
+int segsde_softmax_channels(const float* x, float* out, int b, int c, int64_t hw, int64_t x_sn, int64_t x_sc, int64_t x_sp,
+                            int64_t o_sn, int64_t o_sc, int64_t o_sp, void* stream);
 /* T3 pseudo labels (train.py:644-648): label = argmax_c prob (first maximum), ignore_index where the maximum is 0;
  * count (zero-filled) += #pixels with max >= threshold; pixel_weight (nullable) = weight_scale * count / (B*H*W) at
  * every pixel — the confidence weight stays on the device (the reference reads it with .item()).  prob addressed by
@@ -395,6 +406,52 @@ int segsde_multi_sgd(int n, float* const* p, float* const* g, float* const* mome
                      float momentum, float dampening, float weight_decay, int nesterov, int first_step, void* stream);
 int segsde_multi_clip_grad_norm(int n, float* const* g, const int64_t* numel, float max_norm, double* sum,
                                 float* total_norm, float* coef, void* stream);
+/* Mixed-precision loss scaling (torch.cuda.amp.GradScaler as used at train.py:486-530).  multi_unscale: g *= 1 / scale[0]
+ * in place, found_inf[0] = 1.0 when any gradient element is inf / NaN (found_inf zero-filled by the caller; device
+ * scalars, no host round trip).  amp_update_scale: scale *= backoff on overflow, *= growth after growth_interval clean
+ * steps (growth_tracker: device int). */
+int segsde_multi_unscale(int n, float* const* g, const int64_t* numel, const float* scale, float* found_inf,
+                         void* stream);
+int segsde_amp_update_scale(float* scale, int* growth_tracker, const float* found_inf, float growth_factor,
+                            float backoff_factor, int growth_interval, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Validation / inference path and label-selection scoring (rank 4)
+ * ------------------------------------------------------------------------------------------- */
+/* hist[gt][pred] += 1 over all pixels with 0 <= gt < n_classes (evaluation/metrics.py:12-25, train.py:846-850): pred is
+ * the first arg-max of the logits (addressed by sample / channel / pixel element strides) or, when `pred` is given,
+ * taken from it.  hist: [n_classes][n_classes] int64, accumulated. n_classes <= 32. */
+int segsde_confusion_update(const float* logits, const int64_t* pred, const int64_t* gt, int b, int c, int64_t hw, int64_t sn,
+                            int64_t sc, int64_t sp, int n_classes, int64_t* hist, void* stream);
+/* Eval-mode BatchNorm folded into the preceding convolution: w_out[o][k] = w[o][k] * gamma[o] / sqrt(var[o] + eps),
+ * b_out[o] = beta[o] + (conv_bias[o] - mean[o]) * gamma[o] / sqrt(var[o] + eps); w: [cout][k] (OHWI flattened). */
+int segsde_bn_fold(const float* w, const float* conv_bias, const float* gamma, const float* beta, const float* mean,
+                   const float* var, float eps, int cout, int k, float* w_out, float* b_out, void* stream);
+/* F.adaptive_avg_pool2d / adaptive_max_pool2d on NCHW planar data (label_selection.py:398-426). */
+int segsde_adaptive_pool(const float* x, int nc, int h, int w, int oh, int ow, int is_max, float* y, void* stream);
+/* torch.cdist(f, f, p) for f: [n][d] (label_selection.py:603-606). */
+int segsde_pairwise_distance(const float* f, int n, int64_t d, float p, float* out, void* stream);
+/* iterative_farthest_point (label_selection.py:617-640) in one launch: repeatedly adds the sample with the largest
+ * distance to the selected set.  is_current: [n] 0/1, updated; new_idx / new_dist: [n_new]; count[0] = samples added;
+ * scratch: [n] floats. */
+int segsde_farthest_point(const float* dist, int n, int* is_current, int n_new, int64_t* new_idx, float* new_dist, int* count,
+                          float* scratch, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * On-device input pipeline pieces, NCHW planar fp32
+ * ------------------------------------------------------------------------------------------- */
+/* kornia.filters.GaussianBlur2d((ky,kx), sigma) with reflect border (loader/transformsgpu.py:21-30) as two separable
+ * passes; taps_y / taps_x: normalised 1-D Gaussians on the device, ky / kx odd <= 255; tmp: scratch like x. */
+int segsde_gaussian_blur(const float* x, float* tmp, float* y, int planes, int h, int w, int ky, int kx, const float* taps_y,
+                         const float* taps_x, void* stream);
+/* The four kornia ColorJitter primitives (loader/transformsgpu.py:10-18) fused: brightness (additive), contrast
+ * (multiplicative), saturation (HSV S scale), hue (HSV H shift, radians), each clamped to [0,1], applied in
+ * order4 (a permutation of 0=b,1=c,2=s,3=h).  x / y: [b][3][hw]. */
+int segsde_color_jitter(const float* x, float* y, int b, int64_t hw, float brightness, float contrast, float saturation,
+                        float hue, const int* order4, void* stream);
+/* Scales 1..3 of the loader's image pyramid as exact 2^s x 2^s box means (F.interpolate(mode="area")), one launch;
+ * h, w multiples of 8; any output may be NULL. */
+int segsde_area_pyramid(const float* x, int planes, int h, int w, float* y1, float* y2, float* y3, void* stream);
 
 #ifdef __cplusplus
 }

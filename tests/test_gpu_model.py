@@ -256,15 +256,21 @@ def test_model_tensor_core_path_vs_oracle(contracts):
         ops.USE_TC = False
 
 
+@pytest.mark.parametrize("use_tc", [False, True])
 @pytest.mark.parametrize("name", ["segdec_r50", "pad_r50"])
-def test_seg_decoders_vs_reference_golden(golden, contracts, name):
+def test_seg_decoders_vs_reference_golden(golden, contracts, name, use_tc):
     """JointSegDepthDecoder / PAD (+ SelfAttention gate, bilinear resize, seg heads) and cross_entropy2d through the
-    drop-in API against the reference outputs: logits 2e-4, loss 2e-5, per-parameter gradient norms 3e-2."""
+    drop-in API against the reference outputs.  fp32 CUDA-core route: logits 2e-4, loss 2e-5, per-parameter gradient
+    norms 3e-2.  tcgen05 route (what configs 4 / 5 run): TF32 operands through a train-mode-BatchNorm ResNet-50 at
+    64x96 — logits 3e-2, loss 5e-3, gradient norms 15 % (the same amplification test_gpu_model_tc.py quantifies against
+    the cuDNN-TF32 floor), and the test asserts that the tensor-core kernels are what ran."""
     import improving_segmentation_with_selfsupervised_depth_b200 as P
     from improving_segmentation_with_selfsupervised_depth_b200 import ops
     from improving_segmentation_with_selfsupervised_depth_b200.loss.loss import cross_entropy2d
     from helpers import unpack_named_mask
-    ops.USE_TC = False
+    ops.USE_TC = use_tc
+    t_act, t_loss, t_grad = (3e-2, 5e-3, 0.15) if use_tc else (2e-4, 2e-5, 3e-2)
+    ops.ROUTES = [] if use_tc else None
     models, _ = P.install_dropin()
     H, W, B = 64, 96, 2
     c = contracts[name]
@@ -285,22 +291,31 @@ def test_seg_decoders_vs_reference_golden(golden, contracts, name):
     inputs = {k: v.cuda() for k, v in O.synthetic_inputs(B, H, W, seed=6, labels=True).items()}
     with contextlib.redirect_stdout(io.StringIO()):
         out = model(inputs)
-    assert rel_err(out["semantics"][:, :, ::4, ::4], golden[p + "semantics"]) < 2e-4
+    print(name, "tc" if use_tc else "fp32", "semantics err", rel_err(out["semantics"][:, :, ::4, ::4], golden[p + "semantics"]))
+    assert rel_err(out["semantics"][:, :, ::4, ::4], golden[p + "semantics"]) < t_act
     loss = cross_entropy2d(input=out["semantics"], target=inputs["lbl"])
     if "intermediate_semantics" in out:
-        assert rel_err(out["intermediate_semantics"], golden[p + "intermediate"]) < 2e-4
+        assert rel_err(out["intermediate_semantics"], golden[p + "intermediate"]) < t_act
         for s in range(4):
-            assert rel_err(out[("disp", s)], golden[p + "disp%d" % s]) < 2e-4
+            assert rel_err(out[("disp", s)], golden[p + "disp%d" % s]) < t_act
         loss = ops.add(loss.reshape(1, 1, 1, 1), cross_entropy2d(input=out["intermediate_semantics"],
                                                                  target=inputs["lbl"]).reshape(1, 1, 1, 1)).reshape(()) / 2
-    assert abs(loss.item() - float(golden[p + "loss"])) < 2e-5 * abs(float(golden[p + "loss"]))
+    print(name, "loss err", abs(loss.item() - float(golden[p + "loss"])) / abs(float(golden[p + "loss"])))
+    assert abs(loss.item() - float(golden[p + "loss"])) < t_loss * abs(float(golden[p + "loss"]))
     loss.backward()
+    routes, ops.ROUTES = ops.ROUTES, None
+    ops.USE_TC = False
+    if use_tc:
+        tc = [r for _, r in routes if r.startswith("tc:")]
+        assert len(tc) > 0.8 * len(routes), (len(tc), len(routes))
     params = dict(model.named_parameters())
     names = [str(n) for n in golden[p + "grad_names"]]
-    bad = []
+    bad, worst = [], 0.0
     for n, ref in zip(names, golden[p + "grad_norms"]):
         g = params[n].grad
         v = 0.0 if g is None else g.norm().item()
-        if abs(v - ref) > 3e-2 * ref + 1e-7:
+        worst = max(worst, abs(v - ref) / (ref + 1e-7))
+        if abs(v - ref) > t_grad * ref + 1e-7:
             bad.append((n, v, float(ref)))
+    print(name, "worst grad-norm err", worst)
     assert not bad, bad[:6]

@@ -47,6 +47,26 @@ CASES = [
     (64, 0, 64, 3, 2, 2, False, False, 0, False, 1, 7, 160),
     (64, 0, 128, 3, 1, 1, False, False, 0, True, 2, 9, 130),
 ]
+# The kernel every launch of a case must take, in launch order: fprop, dgrad (one entry per source that gets a
+# gradient; two sources outside the family share ONE generic launch), wgrad.  "generic" = the CUDA-core kernels: the
+# documented fall-back for shapes outside the tensor-core family (dgrad needs Cin % 64 == 0 because Cin is the GEMM N of
+# dgrad-as-fprop; wgrad needs Wo % 32 == 0 because pixels are its GEMM K in 32-pixel boxes).
+ROUTE = [
+    ["tc:conv", "tc:conv", "tc:wgrad"],
+    ["tc:conv", "tc:conv", "tc:wgrad3x3"],
+    ["tc:rowhalo", "tc:rowhalo", "tc:wgrad3x3"],
+    ["tc:conv", "generic", "generic"],                      # Cin = 32; Wo = 40
+    ["tc:conv", "tc:conv", "generic"],                      # Wo = 16
+    ["tc:conv", "tc:conv", "tc:wgrad3x3"],
+    ["tc:conv", "tc:conv", "generic", "tc:wgrad3x3"],       # second source has 32 channels
+    ["tc:conv", "tc:conv", "tc:conv", "tc:wgrad3x3"],
+    ["tc:conv", "tc:conv", "generic"],                      # Wo = 13
+    ["tc:rowhalo", "generic", "tc:wgrad3x3"],               # Cin = 96
+    ["tc:rowhalo", "tc:rowhalo", "tc:rowhalo", "tc:wgrad3x3"],
+    ["tc:rowhalo", "generic", "tc:wgrad3x3"],               # both sources 32 channels: one generic dgrad launch
+    ["tc:rowhalo", "tc:rowhalo", "tc:wgrad3x3"],
+    ["tc:rowhalo", "tc:rowhalo", "generic"],                # Wo = 130
+]
 
 
 def test_tc_is_available():
@@ -54,10 +74,13 @@ def test_tc_is_available():
     assert A.lib().segsde_tc_available() == 1
 
 
-@pytest.mark.parametrize("case", CASES)
-def test_tc_conv_fwd_bwd(case):
+@pytest.mark.parametrize("ci", range(len(CASES)))
+def test_tc_conv_fwd_bwd(ci):
+    """Every case asserts WHICH kernel ran (ops.ROUTES): a silent fall-back to the fp32 CUDA-core kernels would pass the
+    TF32 tolerance trivially."""
     A, ops = _mods()
     ops.USE_TC = True
+    case = CASES[ci]
     c1, c2, co, k, pad, dil, reflect, up1, act, bias, N, H, W = case
     g = torch.Generator().manual_seed(abs(hash(case)) % 997)
     x1 = torch.randn(N, c1, H, W, generator=g).requires_grad_()
@@ -73,12 +96,16 @@ def test_tc_conv_fwd_bwd(case):
     gw = w.detach().cuda().contiguous(memory_format=torch.channels_last).requires_grad_()
     gb = b.detach().cuda().requires_grad_() if bias else None
     n0 = A.launch_count()
-    ops.PROFILE = []
-    gy = ops.conv2d(gx1, gw, gb, x2=gx2, stride=1, pad=pad, dil=dil,
-                    pad_mode=A.PAD_REFLECT if reflect else A.PAD_ZERO, up1=up1, act=act)
-    gy.backward(dy.cuda())
-    torch.cuda.synchronize()
-    ops.PROFILE = None
+    ops.PROFILE, ops.ROUTES = [], []
+    try:
+        gy = ops.conv2d(gx1, gw, gb, x2=gx2, stride=1, pad=pad, dil=dil,
+                        pad_mode=A.PAD_REFLECT if reflect else A.PAD_ZERO, up1=up1, act=act)
+        gy.backward(dy.cuda())
+        torch.cuda.synchronize()
+        routes = [r for _, r in ops.ROUTES]
+    finally:
+        ops.PROFILE, ops.ROUTES = None, None
+    assert routes == ROUTE[ci], (case, routes)
     assert gy.shape == y.shape
     assert rel_err(gy, y) < TOL, "fprop"
 
@@ -117,10 +144,13 @@ def test_tc_conv_stride2(k, cin, cout, H, W):
     gw = w.detach().cuda().contiguous(memory_format=torch.channels_last).requires_grad_()
     ops.PROFILE = []
     ops.PROFILE_DESC = []
+    ops.ROUTES = []
     gy = ops.conv2d(gx, gw, None, stride=2, pad=k // 2)
     gy.backward(dy.cuda())
     torch.cuda.synchronize()
-    ops.PROFILE, ops.PROFILE_DESC = None, None
+    routes = [r for _, r in ops.ROUTES]
+    ops.PROFILE, ops.PROFILE_DESC, ops.ROUTES = None, None, None
+    assert routes == ["tc:conv", "tc:conv", "tc:wgrad"], routes        # fprop, dgrad, wgrad all on the tensor cores
     assert gy.shape == y.shape
     assert rel_err(gy, y) < TOL, "fprop"
     assert rel_err(gx.grad, x.grad) < TOL, "dgrad"
