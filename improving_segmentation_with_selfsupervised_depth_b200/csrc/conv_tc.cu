@@ -228,7 +228,6 @@ __device__ __forceinline__ void epilogue_chunks(uint32_t taddr0, int first, int 
   }
 }
 
-constexpr int STAGES = 5;
 constexpr int MAX_STAT_C = 2048;
 constexpr int A_BYTES = 128 * 128;        // 128 rows x 32 fp32
 constexpr int WSTAGES = 3;                // generic wgrad: 3 stages so that two CTAs share an SM (measured on the
@@ -254,13 +253,25 @@ struct TcConvP {
   double* stats;              // nullable: [0,C) += sum y, [C,2C) += sum y^2 (BatchNorm statistics of the output)
 };
 
-template <int BN>
+// NACC = 1: one M = 128 accumulator per tile (128 pixels).  NACC = 2: a tile is 256 pixels = two M = 128 accumulators that
+// share every weight tile (one (32 ch, BW, 2*BH) activation box per stage): operand bytes per MMA clock drop from
+// (16 + BN/8) KB / 256 clk to (32 + BN/8) KB / 512 clk, i.e. by 1.33x at BN = 128 — the generic kernel is bound by its
+// L2 -> shared-memory operand stream (profiles/r1_generic_kernel.md), so that is its speed-up on layers with enough tiles.
+template <int BN, int NACC>
+__host__ __device__ constexpr int conv_stages() {
+  constexpr int stage = NACC * A_BYTES + BN * 128;
+  constexpr int fit = (MAX_DYN_SMEM - 1024 - EPI_BYTES) / stage;    // the optional statistics buffer is checked at launch
+  return fit > 5 ? 5 : fit;
+}
+
+template <int BN, int NACC>
 __global__ void __launch_bounds__(NT_CONV, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, const TcConvP p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int B_BYTES = BN * 128;
-  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int STAGE_BYTES = NACC * A_BYTES + B_BYTES;
+  constexpr int STAGES = conv_stages<BN, NACC>();
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
   __shared__ uint32_t tmem_base_slot;
@@ -281,7 +292,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
-                 "r"(2 * BN));
+                 "r"(2 * NACC * BN));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
@@ -291,6 +302,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
   const int kchunks = p.Ctot / 32;
   const int kiters = p.kh * p.kw * kchunks;
+  const int TH = NACC * p.BH;               // output rows per tile
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -303,13 +315,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int tn = (int)(t % p.tiles_n); long long q = t / p.tiles_n;
         const int tw = (int)(q % p.tiles_w); q /= p.tiles_w;
         const int th = (int)(q % p.tiles_h); const int n = (int)(q / p.tiles_h);
-        const int w0 = tw * p.BW, h0 = th * p.BH;
+        const int w0 = tw * p.BW, h0 = th * TH;
         for (int tap = 0; tap < p.kh * p.kw; ++tap) {
           const int r = tap / p.kw, s = tap % p.kw;
           const int wi = w0 * p.stride_w - p.pad + s * p.dil, hi = h0 * p.stride - p.pad + r * p.dil;
           for (int kc = 0; kc < kchunks; ++kc) {
             mbar_wait(empty0 + 8 * stage, phase ^ 1);
-            const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES), sb = sa + A_BYTES;
+            const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES), sb = sa + NACC * A_BYTES;
             const uint32_t fb = full0 + 8 * stage;
             mbar_expect_tx(fb, STAGE_BYTES);
             const int c = kc * 32;
@@ -329,16 +341,19 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       mbar_wait(tempty0 + 8 * as, aphase ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + as * BN;
       for (int it = 0; it < kiters; ++it) {
         mbar_wait(full0 + 8 * stage, phase);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES), sb = sa + A_BYTES;
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES), sb = sa + NACC * A_BYTES;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {   // UMMA_K = 8 tf32 = 32 bytes inside the 128-byte swizzle row
-            const uint64_t ad = make_desc(sa + 32 * k, 16, 1024), bd = make_desc(sb + 32 * k, 16, 1024);
-            tc_mma_tf32(d_tmem, ad, bd, idesc, (it | k) != 0);
+          for (int j = 0; j < NACC; ++j) {
+            const uint32_t d_tmem = tmem_base + (as * NACC + j) * BN;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {   // UMMA_K = 8 tf32 = 32 bytes inside the 128-byte swizzle row
+              const uint64_t ad = make_desc(sa + j * A_BYTES + 32 * k, 16, 1024), bd = make_desc(sb + 32 * k, 16, 1024);
+              tc_mma_tf32(d_tmem, ad, bd, idesc, (it | k) != 0);
+            }
           }
           tc_commit(empty0 + 8 * stage);            // frees the smem slot when these MMAs retire
           if (it == kiters - 1) tc_commit(tfull0 + 8 * as);
@@ -358,9 +373,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const int tn = (int)(t % p.tiles_n); long long qq = t / p.tiles_n;
       const int tw = (int)(qq % p.tiles_w); qq /= p.tiles_w;
       const int th = (int)(qq % p.tiles_h); const int n = (int)(qq / p.tiles_h);
+      // NACC == 2: the two warps of a lane quarter take one accumulator (= 128-pixel half of the tile) each;
+      // NACC == 1: they take alternate 32-column chunks of the single accumulator
+      const int jacc = NACC == 2 ? half : 0;
       auto row_ptr = [&](int r) -> float* {
-        const int m = q * 32 + r;
-        const int h = th * p.BH + m / p.BW, w = tw * p.BW + m % p.BW;
+        const int m = jacc * 128 + q * 32 + r;
+        const int h = th * TH + m / p.BW, w = tw * p.BW + m % p.BW;
         return (h < p.Ho && w < p.Wo) ? p.y.p + p.y.off(n, h, w) + tn * BN : nullptr;
       };
       float* dst8[8];
@@ -369,9 +387,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const unsigned valid = __ballot_sync(0xffffffffu, row_ptr(lane) != nullptr);
       mbar_wait(tfull0 + 8 * as, aphase);
       tc_fence_after();
-      epilogue_chunks<(BN / 32 + 1) / 2>(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN, half, 2, BN / 32,
-                                         p.bias ? p.bias + tn * BN : nullptr, p.act, stage, lane, dst8, valid,
-                                         p.stats ? csum : nullptr, tn * BN, p.Cout);
+      if (NACC == 2)
+        epilogue_chunks<BN / 32>(tmem_base + ((uint32_t)(q * 32) << 16) + (as * 2 + jacc) * BN, 0, 1, BN / 32,
+                                 p.bias ? p.bias + tn * BN : nullptr, p.act, stage, lane, dst8, valid,
+                                 p.stats ? csum : nullptr, tn * BN, p.Cout);
+      else
+        epilogue_chunks<(BN / 32 + 1) / 2>(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN, half, 2, BN / 32,
+                                           p.bias ? p.bias + tn * BN : nullptr, p.act, stage, lane, dst8, valid,
+                                           p.stats ? csum : nullptr, tn * BN, p.Cout);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * as);
@@ -383,7 +406,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (p.stats) for (int i = threadIdx.x; i < 2 * p.Cout; i += blockDim.x) atomicAdd(p.stats + i, (double)csum[i]);
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * NACC * BN));
   }
 }
 
@@ -908,21 +931,21 @@ static int num_sms() {
   return n;
 }
 
-template <int BN>
+template <int BN, int NACC>
 static int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcConvP& p, cudaStream_t st) {
-  const int smem = STAGES * (A_BYTES + BN * 128) + 1024 + EPI_BYTES + (p.stats ? 2 * p.Cout * 4 : 0);
+  const int smem = conv_stages<BN, NACC>() * (NACC * A_BYTES + BN * 128) + 1024 + EPI_BYTES + (p.stats ? 2 * p.Cout * 4 : 0);
   static int attr = 0;
   if (smem > MAX_DYN_SMEM) return SEGSDE_E_UNSUPPORTED;
   if (smem > attr) {
-    if (cudaFuncSetAttribute(tc_conv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(tc_conv_kernel<BN, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       cudaGetLastError();
       return SEGSDE_E_UNSUPPORTED;
     }
     attr = smem;
   }
   long long grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  tc_conv_kernel<BN><<<(int)grid, NT_CONV, smem, st>>>(a0, a1, b, p);
-  g_last_tc_kernel = SEGSDE_TC_KERNEL_CONV;
+  tc_conv_kernel<BN, NACC><<<(int)grid, NT_CONV, smem, st>>>(a0, a1, b, p);
+  g_last_tc_kernel = NACC == 2 ? SEGSDE_TC_KERNEL_CONV256 : SEGSDE_TC_KERNEL_CONV;
   return launched();
 }
 template <int BN>
@@ -979,6 +1002,13 @@ static int launch_wgrad3x3(const CUtensorMap& x0, const CUtensorMap& x1, const C
   tc_wgrad3x3_kernel<BN, NSTAGE, MINB><<<p.groups * p.units * p.ntiles * p.splits, NT, smem, st>>>(x0, x1, x0p, x1p, dy, p);
   g_last_tc_kernel = SEGSDE_TC_KERNEL_WGRAD3X3;
   return launched();
+}
+// SEGSDE_TC_M256: 0 = never use 256-pixel tiles in the generic kernel, 1 (default) = when every SM keeps >= 2 tiles,
+// 2 = always (tests)
+static int m256_mode() {
+  static int m = -1;
+  if (m < 0) { const char* e = getenv("SEGSDE_TC_M256"); m = e ? atoi(e) : 1; }
+  return m;
 }
 static int wg3_mode() {     // SEGSDE_TC_WGRAD3: 0 = off, 1 (default) = halo-reuse wgrad for 3x3 / stride 1
   static int m = -1;
@@ -1065,12 +1095,31 @@ extern "C" int segsde_conv2d_fwd_tc_stats(const segsde_nhwc_t* x1, const segsde_
                        : launch_conv3x3<64, 3>(a0, a1, b, r, as_stream(stream));
     }
   }
+  // 256-pixel tiles (two accumulators sharing the weight tile) when that still leaves every SM at least two tiles
+  {
+    const long long tiles2 = (long long)p.tiles_w * cdiv(Ho, 2 * p.BH) * p.N * p.tiles_n;
+    const int mode = m256_mode();
+    if (mode && (mode == 2 || tiles2 >= 2LL * num_sms()) && 2 * p.BH * d->stride <= 256) {
+      TcConvP p2 = p;
+      p2.tiles_h = cdiv(Ho, 2 * p.BH);
+      p2.total_tiles = tiles2;
+      if (make_act_map(&a0, v1, p.BW, 2 * p.BH, d->stride, CU_TENSOR_MAP_SWIZZLE_128B, stride_w) &&
+          (!C2 || make_act_map(&a1, v2, p.BW, 2 * p.BH, d->stride, CU_TENSOR_MAP_SWIZZLE_128B, stride_w)) &&
+          make_w_map(&b, w, d->kh * d->kw * p.Ctot, Cout, BN)) {
+        if (!C2) a1 = a0;
+        int rc = BN == 128 ? launch_conv<128, 2>(a0, a1, b, p2, as_stream(stream))
+                           : (BN == 64 ? launch_conv<64, 2>(a0, a1, b, p2, as_stream(stream))
+                                       : launch_conv<32, 2>(a0, a1, b, p2, as_stream(stream)));
+        if (rc != SEGSDE_E_UNSUPPORTED) return rc;
+      }
+    }
+  }
   if (!make_act_map(&a0, v1, p.BW, p.BH, d->stride, CU_TENSOR_MAP_SWIZZLE_128B, stride_w)) return SEGSDE_E_UNSUPPORTED;
   if (C2) { if (!make_act_map(&a1, v2, p.BW, p.BH, d->stride, CU_TENSOR_MAP_SWIZZLE_128B, stride_w)) return SEGSDE_E_UNSUPPORTED; } else a1 = a0;
   if (!make_w_map(&b, w, d->kh * d->kw * p.Ctot, Cout, BN)) return SEGSDE_E_UNSUPPORTED;
-  if (BN == 128) return launch_conv<128>(a0, a1, b, p, as_stream(stream));
-  if (BN == 64) return launch_conv<64>(a0, a1, b, p, as_stream(stream));
-  return launch_conv<32>(a0, a1, b, p, as_stream(stream));
+  if (BN == 128) return launch_conv<128, 1>(a0, a1, b, p, as_stream(stream));
+  if (BN == 64) return launch_conv<64, 1>(a0, a1, b, p, as_stream(stream));
+  return launch_conv<32, 1>(a0, a1, b, p, as_stream(stream));
 }
 
 // dgrad on the tensor cores = fprop of dy with the transposed/tap-flipped weights; the Python layer prepares

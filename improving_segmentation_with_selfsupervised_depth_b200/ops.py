@@ -25,10 +25,10 @@ PROFILE = None
 
 
 PROFILE_DESC = None   # optional parallel list of human-readable shapes (profiling scripts)
-# when a list, every convolution launch appends (kind, route): route = "tc:<kernel>" (kernel = conv | rowhalo | wgrad |
-# wgrad3x3, the tcgen05 family) or "generic" (CUDA-core fallback for shapes outside the family) — tests assert on it
+# when a list, every convolution launch appends (kind, route): route = "tc:<kernel>" (kernel = conv | conv256 | rowhalo |
+# wgrad | wgrad3x3, the tcgen05 family) or "generic" (CUDA-core fallback for shapes outside the family) — tests assert on it
 ROUTES = None
-_TC_KERNELS = {1: "conv", 2: "rowhalo", 3: "wgrad", 4: "wgrad3x3"}
+_TC_KERNELS = {1: "conv", 2: "rowhalo", 3: "wgrad", 4: "wgrad3x3", 5: "conv256"}
 
 
 def log_route(kind, tc):

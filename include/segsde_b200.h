@@ -141,6 +141,7 @@ int segsde_tc_available(void);
 #define SEGSDE_TC_KERNEL_ROWHALO 2   /* tc_conv3x3_kernel: 3x3 / stride 1, >= 128 px wide, row-halo reuse */
 #define SEGSDE_TC_KERNEL_WGRAD 3     /* tc_wgrad_kernel */
 #define SEGSDE_TC_KERNEL_WGRAD3X3 4  /* tc_wgrad3x3_kernel: halo-reuse weight gradient */
+#define SEGSDE_TC_KERNEL_CONV256 5  /* tc_conv_kernel with 256-pixel tiles (two accumulators share each weight tile) */
 int segsde_tc_last_kernel(void);
 
 /* y = act(x) as a standalone pass (ConvBlock with BatchNorm: conv -> BN -> ELU). */

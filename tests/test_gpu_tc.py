@@ -46,6 +46,10 @@ CASES = [
     (32, 32, 128, 3, 1, 1, True, True, 2, True, 2, 5, 64),
     (64, 0, 64, 3, 2, 2, False, False, 0, False, 1, 7, 160),
     (64, 0, 128, 3, 1, 1, False, False, 0, True, 2, 9, 130),
+    # enough tiles for the generic kernel's 256-pixel tiles (>= 2 per SM): 1x1 wide, 3x3 narrow, concat + odd height
+    (64, 0, 128, 1, 0, 1, False, False, 0, True, 4, 128, 160),
+    (64, 0, 64, 3, 1, 1, False, False, 1, False, 16, 96, 64),
+    (64, 64, 128, 1, 0, 1, False, False, 2, True, 5, 127, 144),
 ]
 # The kernel every launch of a case must take, in launch order: fprop, dgrad (one entry per source that gets a
 # gradient; two sources outside the family share ONE generic launch), wgrad.  "generic" = the CUDA-core kernels: the
@@ -66,6 +70,9 @@ ROUTE = [
     ["tc:rowhalo", "generic", "tc:wgrad3x3"],               # both sources 32 channels: one generic dgrad launch
     ["tc:rowhalo", "tc:rowhalo", "tc:wgrad3x3"],
     ["tc:rowhalo", "tc:rowhalo", "generic"],                # Wo = 130
+    ["tc:conv256", "tc:conv256", "tc:wgrad"],
+    ["tc:conv256", "tc:conv256", "tc:wgrad3x3"],
+    ["tc:conv256", "tc:conv256", "tc:conv256", "generic"],  # Wo = 144 is not a multiple of 32
 ]
 
 
