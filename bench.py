@@ -135,7 +135,7 @@ def reference_trainer(config, B, H, W, seed=1234):
         batch = synthetic(B, H, W, seed, labels=True)
         if torch.cuda.is_available():       # GPU bar: inputs resident, like this repo's `value` (the loaders serve them as-is)
             batch = {k: v.cuda() for k, v in batch.items()}
-        cfg = R.load_cfg(config, H, W, B, "resnet50")
+        cfg = R.load_cfg(config, H, W, B, "resnet50", cudnn_benchmark=True)       # the reference's own default (train.py:176)
         with contextlib.redirect_stdout(io.StringIO()):
             tr = R.make_trainer(cfg, batch, dropin=False)
 

@@ -60,8 +60,10 @@ struct Warp {   // everything the gradient chain needs about one (pixel, frame) 
 
 // Projects the back-projected point of a pixel with camera-space coordinates (cx,cy,cz) into source frame `P`,
 // and samples the three colour planes bilinearly (border padding, align_corners=True).
+// pl[c]: base pointer of colour plane c of the sample (uniform over the warp); the four taps are addressed by 32-bit
+// offsets from it (one IMAD.WIDE per load instead of 64-bit pointer arithmetic per plane).
 template <bool GRAD>
-__device__ __forceinline__ void warp_pixel(const float* __restrict__ src, int H, int W,
+__device__ __forceinline__ void warp_pixel(const float* const (&pl)[3], int H, int W,
                                            const float* P, float cx, float cy, float cz, Warp& o) {
   const float X = P[0] * cx + P[1] * cy + P[2] * cz + P[3];
   const float Y = P[4] * cx + P[5] * cy + P[6] * cz + P[7];
@@ -83,13 +85,12 @@ __device__ __forceinline__ void warp_pixel(const float* __restrict__ src, int H,
   const float ax = ix - fx0, ay = iy - fy0;          // ix - ix_nw
   const float bx = (fx0 + 1.f) - ix, by = (fy0 + 1.f) - iy;  // ix_se - ix
   const float nw = bx * by, ne = ax * by, sw = bx * ay, se = ax * ay;
-  const size_t plane = (size_t)H * W;
-  const float* r0 = src + (size_t)y0 * W;
-  const float* r1 = src + (size_t)y1 * W;
+  const int o0 = y0 * W, o1 = y1 * W;
+  const int onw = o0 + x0, one = o0 + x1, osw = o1 + x0, ose = o1 + x1;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const float vnw = __ldg(r0 + c * plane + x0), vne = __ldg(r0 + c * plane + x1);
-    const float vsw = __ldg(r1 + c * plane + x0), vse = __ldg(r1 + c * plane + x1);
+    const float vnw = __ldg(pl[c] + onw), vne = __ldg(pl[c] + one);
+    const float vsw = __ldg(pl[c] + osw), vse = __ldg(pl[c] + ose);
     o.pred[c] = vnw * nw + vne * ne + vsw * sw + vse * se;
     if (GRAD) {
       o.dpx[c] = mx * ((vne - vnw) * by + (vse - vsw) * ay);
@@ -99,28 +100,33 @@ __device__ __forceinline__ void warp_pixel(const float* __restrict__ src, int H,
   if (GRAD) { o.px = px; o.py = py; o.zinv = rz; }
 }
 
-struct Stats { float mu_x, mu_y, sxx, syy, sxy; };
-
-// SSIM of monodepth_layers.py:240-254 for one channel at one centre from the 3x3 window sums; also returns the statistics.
-__device__ __forceinline__ float ssim_from_sums(float sx, float sy, float sxx, float syy, float sxy, Stats* st) {
-  constexpr float i9 = 1.f / 9.f;      // AvgPool2d(3,1): multiply instead of five fp32 divisions per window
-  const float mu_x = sx * i9, mu_y = sy * i9;
-  const float sig_x = sxx * i9 - mu_x * mu_x;
-  const float sig_y = syy * i9 - mu_y * mu_y;
-  const float sig_xy = sxy * i9 - mu_x * mu_y;
-  const float n = (2.f * mu_x * mu_y + 1e-4f) * (2.f * sig_xy + 9e-4f);
-  const float d = (mu_x * mu_x + mu_y * mu_y + 1e-4f) * (sig_x + sig_y + 9e-4f);
-  if (st) { st->mu_x = mu_x; st->mu_y = mu_y; st->sxx = sig_x; st->syy = sig_y; st->sxy = sig_xy; }
-  return (1.f - __fdividef(n, d)) * 0.5f;   // SSIM in [0,1]: 2 ulp of the quotient is far below the 2e-5 loss tolerance
+// SSIM of monodepth_layers.py:240-254 for one channel at one centre, evaluated on the 3x3 window SUMS (sx = sum x,
+// sxx = sum x^2, sxy = sum x y, ...) instead of the means: with mu = s/9 and sigma = s2/9 - mu^2 both factors of the
+// numerator and of the denominator pick up 81, which cancels in the quotient —
+//   n1 = 2 sx sy + 81 C1            n2 = 2 (9 sxy - sx sy) + 81 C2
+//   d1 = sx^2 + sy^2 + 81 C1        d2 = 9 sxx - sx^2 + 9 syy - sy^2 + 81 C2        ssim = n1 n2 / (d1 d2)
+// — so the five divisions by 9 of AvgPool2d never happen.  The y-only parts (ay = sy^2 + 81 C1, by = 9 syy - sy^2 + 81 C2)
+// are shared by both frames and come in precomputed.
+struct SsimT { float n1, dn, d1, dd, r, iD; };      // dn = n2 - n1, dd = d2 - d1, r = N / D, iD = 1 / D
+__device__ __forceinline__ float ssim_sums(float sx, float sxx, float sxy, float sy, float ay, float by, SsimT* t) {
+  const float p = sx * sy;
+  const float n1 = fmaf(2.f, p, 81.f * 1e-4f);
+  const float n2 = fmaf(2.f, fmaf(9.f, sxy, -p), 81.f * 9e-4f);
+  const float sx2 = sx * sx;
+  const float d1 = sx2 + ay;
+  const float d2 = fmaf(9.f, sxx, by) - sx2;
+  const float iD = __fdividef(1.f, d1 * d2);      // SSIM in [0,1]: 2 ulp here is far below the 2e-5 loss tolerance
+  const float r = (n1 * n2) * iD;
+  if (t) { t->n1 = n1; t->dn = n2 - n1; t->d1 = d1; t->dd = d2 - d1; t->r = r; t->iD = iD; }
+  return fmaf(r, -0.5f, 0.5f);
 }
 
-// left / right neighbour values of v along the strip; ReflectionPad2d(1) at the image border (column -1 = column 1,
-// column W = column W-2) = taking the other neighbour
-__device__ __forceinline__ void neighbours(float v, bool left_edge, bool right_edge, float& l, float& r) {
+// left / right neighbour values of v along the strip.  ReflectionPad2d(1) at the image border (column -1 = column 1,
+// column W = column W-2) costs nothing here: a halo lane whose column lies outside the image evaluates the REFLECTED
+// column instead (xe below), so the lane next to it simply reads its neighbour.
+__device__ __forceinline__ void neighbours(float v, float& l, float& r) {
   l = __shfl_up_sync(FULL, v, 1);
   r = __shfl_down_sync(FULL, v, 1);
-  if (left_edge) l = r;
-  if (right_edge) r = l;
 }
 
 template <int V> struct IC { static constexpr int value = V; };
@@ -140,9 +146,10 @@ __global__ void __launch_bounds__(32, 8) reproj_march_kernel(const ReprojM k) {
   const size_t plane = (size_t)H * W;
   const int x = strip * STRIP - 2 + lane;
   const bool xin = x >= 0 && x < W;
-  const int xc = min(max(x, 0), W - 1);
+  // the column this lane EVALUATES: its own inside the image, the reflected one (-1 -> 1, W -> W-2) in the halo outside;
+  // such a lane only serves as the window neighbour of the border column (it owns no centre: xin is false)
+  const int xe = min(max(reflect_idx(min(max(x, -(W - 1)), 2 * W - 2), W), 0), W - 1);
   const bool own_col = lane >= 2 && lane < 2 + STRIP && x < W;
-  const bool le = (x == 0), re = (x == W - 1);
   // multiplicity of the left / right centre in this column's adjoint of ReflectionPad2d(1)
   const float ml = (x >= 1 && x < W) ? (x == 1 ? 2.f : 1.f) : 0.f;
   const float mr = (x >= 0 && x + 1 < W) ? (x == W - 2 ? 2.f : 1.f) : 0.f;
@@ -169,6 +176,8 @@ __global__ void __launch_bounds__(32, 8) reproj_march_kernel(const ReprojM k) {
 
   const float* tgt_b = k.tgt + (size_t)b * 3 * plane;
   const float* src_b[2] = {k.src[0] + (size_t)b * 3 * plane, k.src[1] + (size_t)b * 3 * plane};
+  const float* const spl[2][3] = {{src_b[0], src_b[0] + plane, src_b[0] + 2 * plane},
+                                  {src_b[1], src_b[1] + plane, src_b[1] + 2 * plane}};
 
   // vertical reflection: window rows of centre c are (c-1, c, c+1) with -1 -> 1 and H -> H-2
   auto vweights = [&](int c, float& wt, float& wb) {
@@ -190,20 +199,20 @@ __global__ void __launch_bounds__(32, 8) reproj_march_kernel(const ReprojM k) {
     auto step = [&](auto ph, int r) {
       constexpr int cur = decltype(ph)::value, p1 = (cur + 2) % 3, p2 = (cur + 1) % 3;
       if (r >= 0 && r < H) {
-        const size_t o = (size_t)r * W + xc;
+        const size_t o = (size_t)r * W + xe;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          const float y = xin ? __ldg(tgt_b + c * plane + o) : 0.f;
+          const float y = __ldg(tgt_b + c * plane + o);
           float yl, yr;
-          neighbours(y, le, re, yl, yr);
+          neighbours(y, yl, yr);
           tv[cur][c] = y;
           yh[cur][c][0] = yl + y + yr;
           yh[cur][c][1] = fmaf(yl, yl, fmaf(y, y, yr * yr));
 #pragma unroll
           for (int f = 0; f < F; ++f) {
-            const float v = xin ? __ldg(src_b[f] + c * plane + o) : 0.f;
+            const float v = __ldg(src_b[f] + c * plane + o);
             float vl, vr;
-            neighbours(v, le, re, vl, vr);
+            neighbours(v, vl, vr);
             sv[cur][f][c] = v;
             xh[cur][f][c][0] = vl + v + vr;
             xh[cur][f][c][1] = fmaf(vl, vl, fmaf(v, v, vr * vr));
@@ -222,13 +231,15 @@ __global__ void __launch_bounds__(32, 8) reproj_march_kernel(const ReprojM k) {
         for (int c = 0; c < 3; ++c) {
           const float sy = yh[p1][c][0] + wt * yh[p2][c][0] + wb * yh[cur][c][0];
           const float syy = yh[p1][c][1] + wt * yh[p2][c][1] + wb * yh[cur][c][1];
+          const float sy2 = sy * sy;
+          const float ay = sy2 + 81.f * 1e-4f, by = fmaf(9.f, syy, 81.f * 9e-4f) - sy2;
 #pragma unroll
           for (int f = 0; f < F; ++f) {
             const float sx = xh[p1][f][c][0] + wt * xh[p2][f][c][0] + wb * xh[cur][f][c][0];
             const float sxx = xh[p1][f][c][1] + wt * xh[p2][f][c][1] + wb * xh[cur][f][c][1];
             const float sxy = xh[p1][f][c][2] + wt * xh[p2][f][c][2] + wb * xh[cur][f][c][2];
             l1_acc[f] += fabsf(tv[p1][c] - sv[p1][f][c]);
-            const float v = ssim_from_sums(sx, sy, sxx, syy, sxy, nullptr);
+            const float v = ssim_sums(sx, sxx, sxy, sy, ay, by, nullptr);
             ssim_acc[f] += fminf(fmaxf(v, 0.f), 1.f);
           }
         }
@@ -249,17 +260,17 @@ __global__ void __launch_bounds__(32, 8) reproj_march_kernel(const ReprojM k) {
   }
 
   // ================= sweeps 1..S: one per scale =================
-  const float rayx[3] = {sIK[0] * (float)x + sIK[2], sIK[3] * (float)x + sIK[5], sIK[6] * (float)x + sIK[8]};
+  const float rayx[3] = {sIK[0] * (float)xe + sIK[2], sIK[3] * (float)xe + sIK[5], sIK[6] * (float)xe + sIK[8]};
   for (int s = 0; s < k.S; ++s) {
     const int hs = k.hs[s], ws = k.ws[s];
     const bool dfull = (hs == H && ws == W);
     const float* dispb = k.disp[s] + (size_t)b * hs * ws;
     // horizontal taps of F.interpolate(bilinear, align_corners=False): scale = in/out, src = max(scale*(dst+0.5)-0.5, 0)
-    int hx0 = xc, hx1 = xc; float hlx = 0.f, hhx = 1.f;
+    int hx0 = xe, hx1 = xe; float hlx = 0.f, hhx = 1.f;
     const float sy_scale = (float)hs / (float)H;
     if (!dfull) {
       const float sx = (float)ws / (float)W;
-      float fx = sx * ((float)xc + 0.5f) - 0.5f; fx = fx < 0.f ? 0.f : fx;
+      float fx = sx * ((float)xe + 0.5f) - 0.5f; fx = fx < 0.f ? 0.f : fx;
       hx0 = (int)fx; hx1 = hx0 + (hx0 < ws - 1 ? 1 : 0);
       hlx = fx - (float)hx0; hhx = 1.f - hlx;
     }
@@ -302,15 +313,15 @@ __global__ void __launch_bounds__(32, 8) reproj_march_kernel(const ReprojM k) {
         float pred[F][3];
 #pragma unroll
         for (int f = 0; f < F; ++f) pred[f][0] = pred[f][1] = pred[f][2] = 0.f;
-        float y3[3] = {0.f, 0.f, 0.f};
-        if (xin) {
-          const size_t o = (size_t)r * W + x;
+        float y3[3];
+        {
+          const size_t o = (size_t)r * W + xe;
 #pragma unroll
           for (int c = 0; c < 3; ++c) y3[c] = __ldg(tgt_b + c * plane + o);
           int y0, y1; float ly, hy;
           vtaps(r, y0, y1, ly, hy);
           float d;
-          if (dfull) d = __ldg(dispb + (size_t)r * ws + x);
+          if (dfull) d = __ldg(dispb + (size_t)r * ws + xe);
           else {
             const float v00 = __ldg(dispb + y0 * ws + hx0), v01 = __ldg(dispb + y0 * ws + hx1);
             const float v10 = __ldg(dispb + y1 * ws + hx0), v11 = __ldg(dispb + y1 * ws + hx1);
@@ -324,7 +335,7 @@ __global__ void __launch_bounds__(32, 8) reproj_march_kernel(const ReprojM k) {
 #pragma unroll
           for (int f = 0; f < F; ++f) {
             Warp wp;
-            warp_pixel<GRAD>(src_b[f], H, W, sP + f * 12, cx, cy, cz, wp);
+            warp_pixel<GRAD>(spl[f], H, W, sP + f * 12, cx, cy, cz, wp);
 #pragma unroll
             for (int c = 0; c < 3; ++c) pred[f][c] = wp.pred[c];
             if (GRAD) {
@@ -345,7 +356,7 @@ __global__ void __launch_bounds__(32, 8) reproj_march_kernel(const ReprojM k) {
         for (int c = 0; c < 3; ++c) {
           const float y = y3[c];
           float yl, yr;
-          neighbours(y, le, re, yl, yr);
+          neighbours(y, yl, yr);
           tg[cur][c] = y;
           yh[cur][c][0] = yl + y + yr;
           yh[cur][c][1] = fmaf(yl, yl, fmaf(y, y, yr * yr));
@@ -353,7 +364,7 @@ __global__ void __launch_bounds__(32, 8) reproj_march_kernel(const ReprojM k) {
           for (int f = 0; f < F; ++f) {
             const float v = pred[f][c];
             float vl, vr;
-            neighbours(v, le, re, vl, vr);
+            neighbours(v, vl, vr);
             pr[cur][f][c] = v;
             xh[cur][f][c][0] = vl + v + vr;
             xh[cur][f][c][1] = fmaf(vl, vl, fmaf(v, v, vr * vr));
@@ -382,28 +393,26 @@ __global__ void __launch_bounds__(32, 8) reproj_march_kernel(const ReprojM k) {
         for (int c = 0; c < 3; ++c) {
           const float sy = yh[p1][c][0] + wt * yh[p2][c][0] + wb * yh[cur][c][0];
           const float syy = yh[p1][c][1] + wt * yh[p2][c][1] + wb * yh[cur][c][1];
+          const float sy2 = sy * sy;
+          const float ay = sy2 + 81.f * 1e-4f, by = fmaf(9.f, syy, 81.f * 9e-4f) - sy2;
 #pragma unroll
           for (int f = 0; f < F; ++f) {
             const float sx = xh[p1][f][c][0] + wt * xh[p2][f][c][0] + wb * xh[cur][f][c][0];
             const float sxx = xh[p1][f][c][1] + wt * xh[p2][f][c][1] + wb * xh[cur][f][c][1];
             const float sxy = xh[p1][f][c][2] + wt * xh[p2][f][c][2] + wb * xh[cur][f][c][2];
             l1_acc[f] += fabsf(tg[p1][c] - pr[p1][f][c]);
-            Stats st;
-            const float v = ssim_from_sums(sx, sy, sxx, syy, sxy, &st);
+            SsimT t;
+            const float v = ssim_sums(sx, sxx, sxy, sy, ay, by, GRAD ? &t : nullptr);
             ssim_acc[f] += fminf(fmaxf(v, 0.f), 1.f);
             if (GRAD) {
-              // d(w_ssim/3 * clamp(ssim)) / d x_i = A + B x_i + C y_i for every x_i of this window; zero where the clamp
-              // is active
-              if (v >= 0.f && v <= 1.f) {
-                const float n1 = 2.f * st.mu_x * st.mu_y + 1e-4f, n2 = 2.f * st.sxy + 9e-4f;
-                const float d1 = st.mu_x * st.mu_x + st.mu_y * st.mu_y + 1e-4f, d2 = st.sxx + st.syy + 9e-4f;
-                const float Nn = n1 * n2;
-                const float iD = __fdividef(1.f, d1 * d2);
-                const float sc = (w_ssim / 3.f) * (1.f / 9.f);
-                coef[f][c][0] = -sc * (st.mu_y * (n2 - n1) * iD - Nn * st.mu_x * (d2 - d1) * iD * iD);
-                coef[f][c][1] = sc * Nn * d1 * iD * iD;
-                coef[f][c][2] = -sc * n1 * iD;
-              }
+              // d(w_ssim/3 * clamp(ssim)) / d x_i = A + B x_i + C y_i for every x_i of this window (zero where the clamp is
+              // active); in the sum form, with k = (w_ssim / 3) / 9 and g = 81 k / D:
+              //   C = -g n1      B = g r d1      A = -(g / 9) (sy (n2 - n1) - r sx (d2 - d1))
+              const float g = (v >= 0.f && v <= 1.f) ? (81.f * (w_ssim / 27.f)) * t.iD : 0.f;
+              const float gr = g * t.r;
+              coef[f][c][0] = (g * (1.f / 9.f)) * fmaf(t.r, sx * t.dd, -(sy * t.dn));
+              coef[f][c][1] = gr * t.d1;
+              coef[f][c][2] = -(g * t.n1);
             }
           }
         }
@@ -423,11 +432,14 @@ __global__ void __launch_bounds__(32, 8) reproj_march_kernel(const ReprojM k) {
               nz[0] = __ldg(noise_s + (((size_t)b * ncand_f) * H + c0) * W + x);
               if (ncand_f == 2) nz[1] = __ldg(noise_s + (((size_t)b * ncand_f + 1) * H + c0) * W + x);
             } else {
+              // tie-break noise ~ 1e-5 N(0,1): Philox4x32-7 (the shortest variant that passes BigCrush) + Box-Muller on
+              // the fast intrinsics — it only has to decorrelate exact ties between the identity candidates
               Philox phx(k.seed, ((unsigned long long)b * H + c0) * W + x, k.offset + s);
-              phx.run();
-              const float rad = sqrtf(-2.f * logf(u01(phx.c[0])));
+#pragma unroll
+              for (int rr = 0; rr < 7; ++rr) phx.round();
+              const float rad = sqrtf(-2.f * __logf(u01(phx.c[0])));
               float sn, cs;
-              sincospif(2.f * u01(phx.c[1]), &sn, &cs);
+              __sincosf(6.283185307179586f * u01(phx.c[1]), &sn, &cs);
               nz[0] = rad * cs * 1e-5f; nz[1] = rad * sn * 1e-5f;
             }
           }
@@ -623,7 +635,8 @@ __global__ void reproj_materialize_kernel(const float* __restrict__ src, const f
   const float r0 = ik[0] * fx + ik[1] * fy + ik[2], r1 = ik[4] * fx + ik[5] * fy + ik[6],
               r2 = ik[8] * fx + ik[9] * fy + ik[10];
   Warp w;
-  if (src) warp_pixel<false>(src + (size_t)b * 3 * plane, H, W, P, depth * r0, depth * r1, depth * r2, w);
+  const float* const mpl[3] = {src + (size_t)b * 3 * plane, src + ((size_t)b * 3 + 1) * plane, src + ((size_t)b * 3 + 2) * plane};
+  if (src) warp_pixel<false>(mpl, H, W, P, depth * r0, depth * r1, depth * r2, w);
   if (sample_o) {
     const float cx = depth * r0, cy = depth * r1, cz = depth * r2;
     const float X = P[0] * cx + P[1] * cy + P[2] * cz + P[3];

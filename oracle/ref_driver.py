@@ -109,7 +109,7 @@ def deactivate():
 # ----------------------------------------------------------------------------------------------------------------------
 # configurations of BASELINE.json, restated from the reference's YAMLs + experiments.py
 # ----------------------------------------------------------------------------------------------------------------------
-def load_cfg(name, H, W, B, backbone="resnet50", n_workers=0):
+def load_cfg(name, H, W, B, backbone="resnet50", n_workers=0, cudnn_benchmark=False):
     """name: dec5 | dec6 | joint | depthmix.  Returns the cfg dict `Trainer.__init__` expects (before its own merge of
     monodepth_options)."""
     yml = {"dec5": "cityscapes_monodepth_highres_dec5_crop.yml", "dec6": "cityscapes_monodepth_highres_dec6_crop.yml",
@@ -120,7 +120,8 @@ def load_cfg(name, H, W, B, backbone="resnet50", n_workers=0):
     m, t, mo = cfg["model"], cfg["training"], cfg["monodepth_options"]
     m.update(backbone_name=backbone, backbone_pretraining="none", depth_pretraining="none", pose_pretraining="none")
     mo.update(height=H, width=W, crop_h=H, crop_w=W)
-    t.update(batch_size=B, val_batch_size=B, n_workers=n_workers, resume=None, n_tensorboard_trainimgs=0, benchmark=False)
+    t.update(batch_size=B, val_batch_size=B, n_workers=n_workers, resume=None, n_tensorboard_trainimgs=0,
+             benchmark=cudnn_benchmark)     # train.py:176 default is True (autotuned cuDNN algorithms); tests pin False
     t.setdefault("save_monodepth_ema", False)
     cfg["data"].setdefault("dataset_seed", 42)
     if name in ("dec5", "dec6"):

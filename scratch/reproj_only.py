@@ -42,4 +42,4 @@ torch.cuda.synchronize()
 ms = sorted(e0.elapsed_time(e1) for _, e0, e1 in A.PROFILE)
 alg = B * (4 * 9 * H * W + (1 if a.fwd else 2) * sum(4 * (H >> s) * (W >> s) for s in range(4)))
 print("reproj fused launch: median %.3f ms  min %.3f ms  (%d iters) loss %.6f  algorithmic %.1f MB -> %.0f GB/s"
-      % (ms[len(ms) // 2], ms[0], len(ms), float(l), alg / 1e6, alg / (ms[len(ms) // 2] * 1e-3) / 1e9))
+      % (ms[len(ms) // 2], ms[0], len(ms), float(l.detach()), alg / 1e6, alg / (ms[len(ms) // 2] * 1e-3) / 1e9))

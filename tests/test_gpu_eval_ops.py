@@ -85,8 +85,10 @@ def test_eval_forward_with_folded_batchnorm(contracts):
     with torch.no_grad():
         ref = O.model_forward(sd, inputs, {"num_layers": 50, "rswd": [False, False, True], "frame_ids": [0, -1, 1]}, O.BNMode(False))
     for s in range(4):
-        assert rel_err(outs[True][("disp", s)], ref[("disp", s)]) < 2e-4, s
-        assert rel_err(outs[True][("disp", s)], outs[False][("disp", s)]) < 1e-4, s
+        assert rel_err(outs[True][("disp", s)], ref[("disp", s)]) < 4e-4, s          # folding re-associates gamma / sqrt(var)
+        assert rel_err(outs[False][("disp", s)], ref[("disp", s)]) < 2e-4, s
+        assert rel_err(outs[True][("disp", s)], outs[False][("disp", s)]) < 4e-4, s
+    assert launches[True] < launches[False]          # the BatchNorm passes are gone
     assert rel_err(outs[True][("cam_T_cam", 0, 1)], ref[("cam_T_cam", 0, 1)]) < 1e-4
 
 
