@@ -264,8 +264,10 @@ class _StemConvFn(torch.autograd.Function):
                                                     C.byref(vy), C.byref(d), A.ptr(stats[0]), st):
                     stats[1] = True
                     done.append(1)
+                    ops.log_route("fprop", True)
                 elif A.try_call("segsde_conv2d_fwd_tc", C.byref(band), None, A.ptr(wpk), None, C.byref(vy), C.byref(d), st):
                     done.append(1)
+                    ops.log_route("fprop", True)
             ops._timed("fprop", flops, launch, desc)
             if done:
                 ctx.save_for_backward(xp, w)
@@ -302,6 +304,7 @@ class _StemConvFn(torch.autograd.Function):
             d = ops._desc(kh, 1, 2, 0, 1, A.PAD_ZERO, False, A.ACT_NONE, False, stride_w=1)
             ops._timed("wgrad", flops, lambda: A.call("segsde_conv2d_wgrad_tc", C.byref(band), None, C.byref(vdz), A.ptr(dwp),
                                                       None, C.byref(d), st), desc)
+            ops.log_route("wgrad", True)
             A.call("segsde_stem_pack_w", A.ptr(dw), A.ptr(dwp), C.c_int(cout), C.c_int(kh), C.c_int(kw), C.c_int(ctot),
                    C.c_int(P), C.c_int(1), st)
             return None, None, dw, None, None, None
@@ -312,8 +315,9 @@ class _StemConvFn(torch.autograd.Function):
 
         def launch_w():
             if A.try_call("segsde_conv2d_wgrad_tc", C.byref(v1), None, C.byref(vdz), A.ptr(dwp), None, C.byref(d), st):
-                return
+                return ops.log_route("wgrad", True)
             A.call("segsde_conv2d_wgrad", C.byref(v1), None, C.byref(vdz), A.ptr(dwp), None, C.byref(d), st)
+            ops.log_route("wgrad", False)
         ops._timed("wgrad", flops, launch_w, desc)
         A.call("segsde_copy_rows", A.ptr(dwp), C.c_int(kpad), A.ptr(dw), C.c_int(k), C.c_int(cout), C.c_int(k), st)
         return None, None, dw, None, None, None
@@ -381,8 +385,9 @@ class _HeadConvFn(torch.autograd.Function):
                 def launch_w():
                     if A.try_call("segsde_conv2d_wgrad_tc", C.byref(v1), None, C.byref(vg), A.ptr(dwz), None,
                                   C.byref(d1), st):
-                        return
+                        return ops.log_route("wgrad", True)
                     A.call("segsde_conv2d_wgrad", C.byref(v1), None, C.byref(vg), A.ptr(dwz), None, C.byref(d1), st)
+                    ops.log_route("wgrad", False)
                 ops._timed("wgrad", 2.0 * n * h * wd * 9 * c, launch_w, desc)
                 dw = torch.empty_like(w)
                 A.call("segsde_copy_rows", A.ptr(dwz), C.c_int(c), A.ptr(dw), C.c_int(c), C.c_int(9), C.c_int(c), st)

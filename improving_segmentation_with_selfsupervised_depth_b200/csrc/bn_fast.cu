@@ -18,14 +18,17 @@ __device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_ca
 
 // Column reductions.  block (32, 8); each warp row covers `ppw` pixels x `cq_w` float4 chunks.
 // MODE 0: S1 = sum (x - s), S2 = sum (x - s)^2 with s = x[pixel 0]; out[2C..3C) = s
-// MODE 1: S1 = sum dz, S2 = sum dz * xhat
+// MODE 1: S1 = sum dz, S2 = sum dz * xhat   (dz = dy masked by ReLU: from the saved output y, or - y.p == NULL, no residual -
+//         RECOMPUTED from x as (x - mean) * (invstd * gamma) + beta > 0, the forward kernels' exact expression, which saves
+//         one full tensor read per pass)
 // MODE 2: dz = dy * act'(y) written out, S1 = sum dz (bias gradient, fp32 atomics into dbias)
 template <int MODE>
 __global__ void __launch_bounds__(256) colreduce_fast_kernel(Rows x, Rows y, Rows dy, Rows dz, long long P, int C,
                                                              const float* __restrict__ mean,
                                                              const float* __restrict__ invstd, int act,
                                                              double* __restrict__ out, float* __restrict__ dbias,
-                                                             long long slab) {
+                                                             long long slab, const float* __restrict__ gamma = nullptr,
+                                                             const float* __restrict__ beta = nullptr) {
   const int cq = C >> 2;
   const int cq_w = cq < 32 ? cq : 32;              // chunks per warp row
   const int ppw = 32 / cq_w;                        // pixels per warp row
@@ -34,10 +37,15 @@ __global__ void __launch_bounds__(256) colreduce_fast_kernel(Rows x, Rows y, Row
   const bool cv = c4 < cq;
   const int c = c4 * 4;
   const long long pbeg = (long long)blockIdx.x * slab, pend = min(P, pbeg + slab);
-  float4 sh = make_float4(0.f, 0.f, 0.f, 0.f), mu = sh, is = sh;
+  float4 sh = make_float4(0.f, 0.f, 0.f, 0.f), mu = sh, is = sh, sc = sh, bt = sh;
   if (cv) {
     if (MODE == 0) sh = ld4(x.p + c);
-    if (MODE == 1) { mu = ld4(mean + c); is = ld4(invstd + c); }
+    if (MODE == 1) {
+      mu = ld4(mean + c); is = ld4(invstd + c);
+      const float4 g4 = gamma ? ld4(gamma + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+      sc = make_float4(is.x * g4.x, is.y * g4.y, is.z * g4.z, is.w * g4.w);
+      if (beta) bt = ld4(beta + c);
+    }
   }
   double d1[4] = {0, 0, 0, 0}, d2[4] = {0, 0, 0, 0};
   float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), a2 = a1;
@@ -53,7 +61,12 @@ __global__ void __launch_bounds__(256) colreduce_fast_kernel(Rows x, Rows y, Row
         float4 g = ld4(dy.p + p * dy.ld + c);
         const float4 v = ld4(x.p + p * x.ld + c);
         if (act == SEGSDE_ACT_RELU) {
-          const float4 o = ld4(y.p + p * y.ld + c);
+          float4 o;
+          if (y.p) o = ld4(y.p + p * y.ld + c);
+          else {
+            o.x = (v.x - mu.x) * sc.x + bt.x; o.y = (v.y - mu.y) * sc.y + bt.y;
+            o.z = (v.z - mu.z) * sc.z + bt.z; o.w = (v.w - mu.w) * sc.w + bt.w;
+          }
           g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f; g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
         }
         a1.x += g.x; a1.y += g.y; a1.z += g.z; a1.w += g.w;
@@ -176,7 +189,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_fast_kernel(Rows x, Rows y, 
                                                                 const float* __restrict__ mean,
                                                                 const float* __restrict__ invstd,
                                                                 const float* __restrict__ gamma, int relu, int training,
-                                                                const double* __restrict__ red, float inv_count) {
+                                                                const double* __restrict__ red, float inv_count,
+                                                                const float* __restrict__ beta) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
     long long p; int c4;
     if (cq_shift >= 0) { p = i >> cq_shift; c4 = (int)(i & (cq - 1)); } else { p = i / cq; c4 = (int)(i - p * cq); }
@@ -185,7 +199,15 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_fast_kernel(Rows x, Rows y, 
     { const float4 t = ld4(dy.p + p * dy.ld + c); g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w; }
     { const float4 t = ld4(x.p + p * x.ld + c); xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w; }
     if (relu) {
-      const float4 t = ld4(y.p + p * y.ld + c);
+      float4 t;
+      if (y.p) t = ld4(y.p + p * y.ld + c);
+      else {       // recompute the forward value (no residual): same expression as bn_apply*_fast_kernel
+        const float4 m = ld4(mean + c), is4 = ld4(invstd + c);
+        const float4 g4 = gamma ? ld4(gamma + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+        const float4 b4 = beta ? ld4(beta + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        t.x = (xv[0] - m.x) * (is4.x * g4.x) + b4.x; t.y = (xv[1] - m.y) * (is4.y * g4.y) + b4.y;
+        t.z = (xv[2] - m.z) * (is4.z * g4.z) + b4.z; t.w = (xv[3] - m.w) * (is4.w * g4.w) + b4.w;
+      }
       if (!(t.x > 0.f)) g[0] = 0.f; if (!(t.y > 0.f)) g[1] = 0.f; if (!(t.z > 0.f)) g[2] = 0.f; if (!(t.w > 0.f)) g[3] = 0.f;
     }
 #pragma unroll
@@ -231,13 +253,13 @@ int bn_stats_fast(const View& x, double* sums, cudaStream_t st) {
   return launched();
 }
 int bn_bwd_reduce_fast(const View& x, const View& y, const View& dy, const float* mean, const float* invstd, int act,
-                       double* red, cudaStream_t st) {
+                       double* red, cudaStream_t st, const float* gamma, const float* beta) {
   const long long P = (long long)x.n * x.h * x.w;
   dim3 grid; long long slab;
   reduce_geometry(P, x.c, grid, slab);
   Rows none; none.p = nullptr; none.ld = 0;
   colreduce_fast_kernel<1><<<grid, dim3(32, 8), 0, st>>>(rows_of(x), y.p ? rows_of(y) : none, rows_of(dy), none, P, x.c, mean,
-                                                        invstd, act, red, nullptr, slab);
+                                                        invstd, act, red, nullptr, slab, gamma, beta);
   return launched();
 }
 int act_bwd_bias_fast(const View& y, const View& dy, const View& dz, int act, float* dbias, cudaStream_t st) {
@@ -275,7 +297,7 @@ int bn_apply_train_fast(const View& x, const View& res, const View& y, const dou
 }
 int bn_bwd_apply_fast(const View& x, const View& y, const View& dy, const View& dx, const View& dres, const float* mean,
                       const float* invstd, const float* gamma, int relu, int training, const double* red, long long count,
-                      cudaStream_t st) {
+                      cudaStream_t st, const float* beta) {
   const long long P = (long long)x.n * x.h * x.w;
   const int cq = x.c / 4;
   const long long total4 = P * cq;
@@ -284,7 +306,7 @@ int bn_bwd_apply_fast(const View& x, const View& y, const View& dy, const View& 
   bn_bwd_apply_fast_kernel<<<(unsigned)blocks, 256, 0, st>>>(rows_of(x), y.p ? rows_of(y) : none, rows_of(dy),
                                                             dx.p ? rows_of(dx) : none, dres.p ? rows_of(dres) : none, total4, cq,
                                                             shift_of(cq), x.c, mean, invstd, gamma, relu, training, red,
-                                                            (float)(1.0 / (double)count));
+                                                            (float)(1.0 / (double)count), beta);
   return launched();
 }
 

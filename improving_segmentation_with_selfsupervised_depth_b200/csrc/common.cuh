@@ -130,7 +130,7 @@ bool pix_contig(const View& v);
 bool fast_reduce_ok(const View& x);
 int bn_stats_fast(const View& x, double* sums, cudaStream_t st);
 int bn_bwd_reduce_fast(const View& x, const View& y, const View& dy, const float* mean, const float* invstd, int act,
-                       double* red, cudaStream_t st);
+                       double* red, cudaStream_t st, const float* gamma, const float* beta);
 int act_bwd_bias_fast(const View& y, const View& dy, const View& dz, int act, float* dbias, cudaStream_t st);
 int bn_apply_fast(const View& x, const View& res, const View& y, const float* mean, const float* invstd, const float* gamma,
                   const float* beta, int act, cudaStream_t st);
@@ -139,6 +139,6 @@ int bn_apply_train_fast(const View& x, const View& res, const View& y, const dou
                         float* rmean, float* rvar, cudaStream_t st);
 int bn_bwd_apply_fast(const View& x, const View& y, const View& dy, const View& dx, const View& dres, const float* mean,
                       const float* invstd, const float* gamma, int relu, int training, const double* red, long long count,
-                      cudaStream_t st);
+                      cudaStream_t st, const float* beta);
 
 }  // namespace segsde

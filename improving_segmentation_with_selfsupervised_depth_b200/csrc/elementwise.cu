@@ -46,12 +46,14 @@ static inline int ew_blocks(const View& v, int vec) {
 template <int MODE>
 __global__ void __launch_bounds__(256) chan_reduce_kernel(View x, View y, View dy, const float* __restrict__ mean,
                                                           const float* __restrict__ invstd, int relu,
-                                                          double* __restrict__ out, long long slab) {
+                                                          double* __restrict__ out, long long slab,
+                                                          const float* __restrict__ gamma = nullptr,
+                                                          const float* __restrict__ beta = nullptr) {
   const int c = blockIdx.x * 32 + threadIdx.x;
   const long long P = (long long)x.n * x.h * x.w;
   const long long pbeg = (long long)blockIdx.y * slab, pend = min(P, pbeg + slab);
-  float mu = 0.f, is = 0.f;
-  if (MODE == 1 && c < x.c) { mu = mean[c]; is = invstd[c]; }
+  float mu = 0.f, is = 0.f, sc = 0.f, bt = 0.f;
+  if (MODE == 1 && c < x.c) { mu = mean[c]; is = invstd[c]; sc = is * (gamma ? gamma[c] : 1.f); bt = beta ? beta[c] : 0.f; }
   // fp64 accumulation: var = E[x^2] - mean^2 cancels catastrophically in fp32 when var << mean^2
   // (e.g. ASPPPooling's BatchNorm over B x 256 x 1 x 1 with similar samples); float*float is exact in double.
   double d0 = 0.0, d1 = 0.0;
@@ -63,7 +65,10 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(View x, View y, View d
       if (MODE == 0) { d0 += (double)xv; d1 += (double)xv * (double)xv; }
       else {
         float g = dy.p[dy.off(n, h, w) + c];
-        if (relu && !(y.p[y.off(n, h, w) + c] > 0.f)) g = 0.f;
+        if (relu) {      // mask from the saved output, or recomputed from x (no residual; the forward's exact expression)
+          const float o = y.p ? y.p[y.off(n, h, w) + c] : (xv - mu) * sc + bt;
+          if (!(o > 0.f)) g = 0.f;
+        }
         d0 += (double)g; d1 += (double)g * (double)((xv - mu) * is);
       }
     }
@@ -128,19 +133,22 @@ template <int VEC>
 __global__ void bn_bwd_apply_kernel(View x, View y, View dy, const float* __restrict__ mean,
                                     const float* __restrict__ invstd, const float* __restrict__ gamma, int relu,
                                     int training, const double* __restrict__ red, float inv_count, View dx,
-                                    View dres) {
+                                    View dres, const float* __restrict__ beta) {
   EW_DECOMP(x, VEC)
   Vec<VEC> xv, yv, gv, o;
   xv.load(x.p + x.off(n_, h_, w_) + c_);
   gv.load(dy.p + dy.off(n_, h_, w_) + c_);
-  if (relu) yv.load(y.p + y.off(n_, h_, w_) + c_);
+  if (relu && y.p) yv.load(y.p + y.off(n_, h_, w_) + c_);
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
     const int c = c_ + i;
     float g = gv.v[i];
-    if (relu && !(yv.v[i] > 0.f)) g = 0.f;
-    gv.v[i] = g;
     const float sc = invstd[c] * (gamma ? gamma[c] : 1.f);
+    if (relu) {
+      const float fwd = y.p ? yv.v[i] : (xv.v[i] - mean[c]) * sc + (beta ? beta[c] : 0.f);
+      if (!(fwd > 0.f)) g = 0.f;
+    }
+    gv.v[i] = g;
     if (training) {
       const float xh = (xv.v[i] - mean[c]) * invstd[c];
       const float m0 = (float)red[c] * inv_count, m1 = (float)red[x.c + c] * inv_count;
@@ -453,38 +461,38 @@ extern "C" int segsde_bn_apply_train(const segsde_nhwc_t* x, const double* sums,
   return segsde_bn_apply(x, mean, invstd, gamma, beta, residual, y, act, stream);
 }
 extern "C" int segsde_bn_bwd_reduce(const segsde_nhwc_t* x, const segsde_nhwc_t* y, const segsde_nhwc_t* dy,
-                                    const float* mean, const float* invstd, int act, double* red, void* stream) {
+                                    const float* mean, const float* invstd, const float* gamma, const float* beta,
+                                    int act, double* red, void* stream) {
   if (!x || !x->ptr || !dy || !dy->ptr || !mean || !invstd || !red) return SEGSDE_E_ARG;
   const int relu = act == SEGSDE_ACT_RELU;
-  if (relu && (!y || !y->ptr)) return SEGSDE_E_ARG;
   View vx = mk(x), vy = mk(y), vd = mk(dy);
   if (!same_shape(vx, vd)) return SEGSDE_E_ARG;
-  if (fast_reduce_ok(vx) && pix_contig(vd) && (!relu || pix_contig(vy)))
-    return bn_bwd_reduce_fast(vx, vy, vd, mean, invstd, act, red, as_stream(stream));
+  if (fast_reduce_ok(vx) && pix_contig(vd) && (!relu || !vy.p || pix_contig(vy)))
+    return bn_bwd_reduce_fast(vx, vy, vd, mean, invstd, act, red, as_stream(stream), gamma, beta);
   int ns; const long long slab = slab_for(vx, ns);
   dim3 grid(cdiv(vx.c, 32), ns), block(32, 8);
-  chan_reduce_kernel<1><<<grid, block, 0, as_stream(stream)>>>(vx, vy, vd, mean, invstd, relu, red, slab);
+  chan_reduce_kernel<1><<<grid, block, 0, as_stream(stream)>>>(vx, vy, vd, mean, invstd, relu, red, slab, gamma, beta);
   return launched();
 }
 extern "C" int segsde_bn_bwd_apply(const segsde_nhwc_t* x, const segsde_nhwc_t* y, const segsde_nhwc_t* dy,
-                                   const float* mean, const float* invstd, const float* gamma, int act,
-                                   int training, const double* red, int64_t count, const segsde_nhwc_t* dx,
+                                   const float* mean, const float* invstd, const float* gamma, const float* beta,
+                                   int act, int training, const double* red, int64_t count, const segsde_nhwc_t* dx,
                                    const segsde_nhwc_t* dres, float* dgamma, float* dbeta, void* stream) {
   if (!x || !x->ptr || !dy || !dy->ptr || !mean || !invstd || !red || count < 1) return SEGSDE_E_ARG;
   const int relu = act == SEGSDE_ACT_RELU;
   View vx = mk(x), vy = mk(y), vd = mk(dy), vdx = mk(dx), vdr = mk(dres);
-  if (relu && !vy.p) return SEGSDE_E_ARG;
+  if (relu && !vy.p && vdr.p) return SEGSDE_E_ARG;      // with a residual the mask needs the saved output
   int rc = SEGSDE_OK;
-  const bool fast = pix_contig(vx) && pix_contig(vd) && (!relu || pix_contig(vy)) && (!vdx.p || pix_contig(vdx)) &&
+  const bool fast = pix_contig(vx) && pix_contig(vd) && (!relu || !vy.p || pix_contig(vy)) && (!vdx.p || pix_contig(vdx)) &&
                     (!vdr.p || pix_contig(vdr));
   if ((vdx.p || vdr.p) && fast) {
-    rc = bn_bwd_apply_fast(vx, vy, vd, vdx, vdr, mean, invstd, gamma, relu, training, red, count, as_stream(stream));
+    rc = bn_bwd_apply_fast(vx, vy, vd, vdx, vdr, mean, invstd, gamma, relu, training, red, count, as_stream(stream), beta);
     if (rc) return rc;
   } else if (vdx.p || vdr.p) {
-    const bool v4 = vec4_ok(vx) && vec4_ok(vd) && (!relu || vec4_ok(vy)) && (!vdx.p || vec4_ok(vdx)) &&
+    const bool v4 = vec4_ok(vx) && vec4_ok(vd) && (!relu || !vy.p || vec4_ok(vy)) && (!vdx.p || vec4_ok(vdx)) &&
                     (!vdr.p || vec4_ok(vdr));
     DISPATCH_VEC(v4, bn_bwd_apply_kernel, vx, vx, vy, vd, mean, invstd, gamma, relu, training, red,
-                 (float)(1.0 / (double)count), vdx, vdr);
+                 (float)(1.0 / (double)count), vdx, vdr, beta);
     rc = launched();
     if (rc) return rc;
   }

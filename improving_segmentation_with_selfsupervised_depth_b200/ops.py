@@ -193,13 +193,15 @@ class _BatchNormFn(torch.autograd.Function):
                    A.ptr(mean), A.ptr(invstd), st)
             A.call("segsde_bn_apply", C.byref(view(x)), A.ptr(mean), A.ptr(invstd), A.ptr(gw), A.ptr(gb), vres,
                    C.byref(view(y)), C.c_int(act), st)
-        ctx.save_for_backward(x, y if act == A.ACT_RELU else None, mean, invstd, gw)
+        # ReLU mask for the backward pass: with a residual it needs the saved output; without one the kernels recompute
+        # it from x (one tensor read less in each of the two backward passes)
+        ctx.save_for_backward(x, y if (act == A.ACT_RELU and residual is not None) else None, mean, invstd, gw, gb)
         ctx.cfg = (training, act, residual is not None)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, y, mean, invstd, gw = ctx.saved_tensors
+        x, y, mean, invstd, gw, gb = ctx.saved_tensors
         training, act, has_res = ctx.cfg
         dy = as_cl(dy)
         n, c, h, w = x.shape
@@ -207,14 +209,14 @@ class _BatchNormFn(torch.autograd.Function):
         red = zeros_f64(2 * c, dev)
         vy = view(y) if y is not None else None
         A.call("segsde_bn_bwd_reduce", C.byref(view(x)), _ref(vy), C.byref(view(dy)), A.ptr(mean), A.ptr(invstd),
-               C.c_int(act), A.ptr(red), st)
+               A.ptr(gw), A.ptr(gb), C.c_int(act), A.ptr(red), st)
         need_x, need_w, need_b, need_r = ctx.needs_input_grad[:4]
         dx = cl_empty(n, c, h, w, dev) if need_x else None
         dres = cl_empty(n, c, h, w, dev) if (has_res and need_r) else None
         dgamma = zeros_f32(c, dev) if need_w else None
         dbeta = zeros_f32(c, dev) if need_b else None
         A.call("segsde_bn_bwd_apply", C.byref(view(x)), _ref(vy), C.byref(view(dy)), A.ptr(mean), A.ptr(invstd),
-               A.ptr(gw), C.c_int(act), C.c_int(1 if training else 0), A.ptr(red), C.c_int64(n * h * w),
+               A.ptr(gw), A.ptr(gb), C.c_int(act), C.c_int(1 if training else 0), A.ptr(red), C.c_int64(n * h * w),
                _ref(view(dx)) if dx is not None else None, _ref(view(dres)) if dres is not None else None,
                A.ptr(dgamma), A.ptr(dbeta), st)
         return dx, dgamma, dbeta, dres, None, None, None, None, None, None, None

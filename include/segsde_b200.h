@@ -177,14 +177,16 @@ int segsde_bn_apply_train(const segsde_nhwc_t* x, const double* sums, int64_t co
                           const float* gamma, const float* beta, const segsde_nhwc_t* residual,
                           const segsde_nhwc_t* y, int act, float* mean, float* invstd, float* running_mean,
                           float* running_var, void* stream);
-/* Backward, step 1: red[0..C)=sum dz, red[C..2C)=sum dz*xhat (fp64, zero-filled) where
- * dz = dy * relu'(y) (act==RELU needs y). */
+/* Backward, step 1: red[0..C)=sum dz, red[C..2C)=sum dz*xhat (fp64, zero-filled) where dz = dy * relu'(out).
+ * act==RELU: the mask comes from the saved output y, or — y == NULL, layer WITHOUT a residual — is recomputed from x as
+ * (x - mean) * (invstd * gamma) + beta > 0 (the forward kernels' exact expression): one full tensor read less. */
 int segsde_bn_bwd_reduce(const segsde_nhwc_t* x, const segsde_nhwc_t* y, const segsde_nhwc_t* dy,
-                         const float* mean, const float* invstd, int act, double* red, void* stream);
+                         const float* mean, const float* invstd, const float* gamma, const float* beta, int act,
+                         double* red, void* stream);
 /* Backward, step 2: dx (train: full formula; eval: dz*gamma*invstd), dres = dz (may be NULL),
- * dgamma/dbeta (+=, may be NULL) from red. */
+ * dgamma/dbeta (+=, may be NULL) from red.  y == NULL with act==RELU as above (not together with dres). */
 int segsde_bn_bwd_apply(const segsde_nhwc_t* x, const segsde_nhwc_t* y, const segsde_nhwc_t* dy,
-                        const float* mean, const float* invstd, const float* gamma, int act,
+                        const float* mean, const float* invstd, const float* gamma, const float* beta, int act,
                         int training, const double* red, int64_t count, const segsde_nhwc_t* dx,
                         const segsde_nhwc_t* dres, float* dgamma, float* dbeta, void* stream);
 

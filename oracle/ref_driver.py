@@ -199,12 +199,12 @@ class SyntheticLoader(torch.utils.data.Dataset):
             out[k] = v[b]
         if self.onehot and "lbl" in self.batch:
             lbl = self.batch["lbl"][b]
-            oh = torch.zeros(self.n_classes, *lbl.shape)
+            oh = torch.zeros(self.n_classes, *lbl.shape, device=lbl.device)
             valid = lbl != self.ignore_index
             oh.scatter_(0, lbl.clamp(0, self.n_classes - 1)[None], 1.0)
             oh *= valid[None]
             out["onehot_lbl"] = oh
-            out["is_labeled"] = torch.tensor(True)
+            out["is_labeled"] = torch.tensor(i % 2 == 0)        # half of the samples keep the teacher's own softmax
         out["filename"] = "synthetic_%d" % i
         return out
 

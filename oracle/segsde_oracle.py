@@ -34,11 +34,11 @@ def disp_to_depth(disp, min_depth, max_depth):
 def backproject(depth, inv_K):
     """BackprojectDepth.forward, models/monodepth_layers.py:169-174 (pixel grid built at :155-167)."""
     B, _, H, W = depth.shape
-    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32),
-                            indexing="ij")
-    pix = torch.stack([xs.reshape(-1), ys.reshape(-1), torch.ones(H * W)], 0).unsqueeze(0).expand(B, 3, H * W)
+    dev, dt = depth.device, depth.dtype       # the reference keeps these buffers on the module's device (:155-167)
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=dt, device=dev), torch.arange(W, dtype=dt, device=dev), indexing="ij")
+    pix = torch.stack([xs.reshape(-1), ys.reshape(-1), torch.ones(H * W, dtype=dt, device=dev)], 0).unsqueeze(0).expand(B, 3, H * W)
     cam = torch.matmul(inv_K[:, :3, :3], pix) * depth.reshape(B, 1, -1)
-    return torch.cat([cam, torch.ones(B, 1, H * W)], 1)
+    return torch.cat([cam, torch.ones(B, 1, H * W, dtype=dt, device=dev)], 1)
 
 
 def project(points, K, T, H, W, eps=1e-7):
@@ -48,7 +48,7 @@ def project(points, K, T, H, W, eps=1e-7):
     cam = torch.matmul(P, points)
     pix = cam[:, :2, :] / (cam[:, 2, :].unsqueeze(1) + eps)
     pix = pix.view(B, 2, H, W).permute(0, 2, 3, 1)
-    norm = torch.tensor([W - 1, H - 1], dtype=torch.float32)
+    norm = torch.tensor([W - 1, H - 1], dtype=pix.dtype, device=pix.device)
     return (pix / norm - 0.5) * 2
 
 

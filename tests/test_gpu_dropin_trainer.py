@@ -160,16 +160,20 @@ def test_loss_curve_100_steps():
     assert mean(d_tf) < 3 * mean(d_c) + 1e-3, (mean(d_tf), mean(d_c))
 
 
-@pytest.mark.parametrize("name,keys", [
-    ("dec6", ["mono_loss", "feat_dist_loss", "total_loss"]),
-    ("joint", ["segmentation_loss", "mono_loss", "total_loss"]),
-    ("depthmix", ["segmentation_loss", "segmentation_total_loss", "mono_total_loss", "total_loss"])])
-def test_config_steps(name, keys):
+@pytest.mark.parametrize("name,keys,tf32,steps,tol", [
+    ("dec6", ["mono_loss", "feat_dist_loss", "total_loss"], False, 3, 2e-3),
+    ("joint", ["segmentation_loss", "mono_loss", "total_loss"], False, 3, 2e-3),
+    ("depthmix", ["segmentation_loss", "segmentation_total_loss", "mono_total_loss", "total_loss"], False, 3, 2e-3),
+    # the tcgen05 route of the PAD multi-task decoder (what bench.py --config joint runs) against the reference with
+    # cuDNN TF32 convolutions: first step only (both sides carry TF32 operand rounding, amplified by train-mode BatchNorm
+    # on a 4 x 8-pixel bottleneck), 5 % on every loss of the step
+    ("joint", ["segmentation_loss", "mono_loss", "total_loss"], True, 1, 5e-2)])
+def test_config_steps(name, keys, tf32, steps, tol):
     R = _driver()
     B, H, W = 2, 64, 128
     cfg = R.load_cfg(name, H, W, B, "resnet50")
     batch = _batch(B, H, W, seed=22)
-    ref, sd0, masks = _run(R, cfg, batch, 3, dropin=False)
-    own, _, _ = _run(R, cfg, batch, 3, dropin=True, init_sd=sd0, masks=masks)
-    worst = _curves(name, ref, own, keys)
-    assert worst < 2e-3, worst
+    ref, sd0, masks = _run(R, cfg, batch, steps, dropin=False, tf32=tf32)
+    own, _, _ = _run(R, cfg, batch, steps, dropin=True, init_sd=sd0, masks=masks, tf32=tf32)
+    worst = _curves(name + ("_tf32" if tf32 else ""), ref, own, keys)
+    assert worst < tol, worst

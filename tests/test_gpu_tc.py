@@ -157,7 +157,8 @@ def test_tc_conv_stride2(k, cin, cout, H, W):
     torch.cuda.synchronize()
     routes = [r for _, r in ops.ROUTES]
     ops.PROFILE, ops.PROFILE_DESC, ops.ROUTES = None, None, None
-    assert routes == ["tc:conv", "tc:conv", "tc:wgrad"], routes        # fprop, dgrad, wgrad all on the tensor cores
+    # fprop and dgrad on the tensor cores; wgrad too when the output width is a multiple of its 32-pixel GEMM-K boxes
+    assert routes == ["tc:conv", "tc:conv", "tc:wgrad" if (W // 2) % 32 == 0 else "generic"], routes
     assert gy.shape == y.shape
     assert rel_err(gy, y) < TOL, "fprop"
     assert rel_err(gx.grad, x.grad) < TOL, "dgrad"
