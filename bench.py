@@ -132,12 +132,13 @@ def reference_trainer(config, B, H, W, seed=1234):
     import ref_driver as R
     if R.available():
         import torch
-        batch = synthetic(B, H, W, seed, labels=True)
-        if torch.cuda.is_available():       # GPU bar: inputs resident, like this repo's `value` (the loaders serve them as-is)
-            batch = {k: v.cuda() for k, v in batch.items()}
+        host_batch = synthetic(B, H, W, seed, labels=True)
+        batch = host_batch
+        if torch.cuda.is_available():       # GPU bar: the labeled step inputs resident, like this repo's `value`; the
+            batch = {k: v.cuda() for k, v in host_batch.items()}     # unlabeled loader (depthmix) stays the reference's own
         cfg = R.load_cfg(config, H, W, B, "resnet50", cudnn_benchmark=True)       # the reference's own default (train.py:176)
         with contextlib.redirect_stdout(io.StringIO()):
-            tr = R.make_trainer(cfg, batch, dropin=False)
+            tr = R.make_trainer(cfg, host_batch, dropin=False)      # pinned-memory DataLoader path of train.py:244-262
 
         def step(i=[0]):
             inputs = {k: (v.clone() if hasattr(v, "clone") else v) for k, v in batch.items()}

@@ -23,6 +23,10 @@ from . import ops
 
 TC_STRIDE2_FPROP = True      # 3x3/s2 forward on the tensor cores via TMA element strides
 
+# stride-2 3x3 dgrad as four phase convolutions instead of zero-stuffing (SEGSDE_PHASE_DGRAD=0 restores round 1's form)
+PHASE_DGRAD_S2 = os.environ.get("SEGSDE_PHASE_DGRAD", "1") != "0"
+
+
 def _tc_enabled():
     return ops.USE_TC and A.lib().segsde_tc_available() == 1
 
@@ -124,14 +128,47 @@ class _Conv2dFn(torch.autograd.Function):
         c2 = x2e.shape[1] if x2e is not None else 0
         flops_scale = 1.0
         dz_s, d_s = None, None      # the strided dz / descriptor: wgrad takes them directly (no zero-stuffing)
+        phase_dx1 = None
+        if (stride == 2 and tc_ch and mode_e == A.PAD_ZERO and not up_e and not nchw and need1 and x2e is None and kh == 3
+                and kw == 3 and pad_e == 1 and dil == 1 and c1 % 64 == 0 and cout % 32 == 0 and wo >= 8 and _tc_enabled()
+                and PHASE_DGRAD_S2):
+            # dgrad of a 3x3 / stride-2 convolution as four phase convolutions (1, 2, 2 and 4 taps) of dz, each writing
+            # one (row parity, column parity) sub-grid of dx: 9/4 taps per input pixel instead of 9 over the zero-stuffed
+            # gradient, and no fill + strided copy of the stuffed buffer
+            gx = ops.cl_empty(*x1e.shape, dev)
+            ok = True
+            for a in (0, 1):
+                for b_ in (0, 1):
+                    sub = gx[:, :, a::2, b_::2]
+                    if sub.shape[2] == 0 or sub.shape[3] == 0:
+                        continue
+                    wt = torch.empty(c1 * (1 + a) * (1 + b_) * cout, device=dev, dtype=torch.float32)
+                    A.call("segsde_weight_phase_s2", A.ptr(w), A.ptr(wt), C.c_int(cout), C.c_int(ctot), C.c_int(0), C.c_int(c1),
+                           C.c_int(a), C.c_int(b_), st)
+                    dd = ops._desc(1 + a, 1 + b_, 1, 0, 1, A.PAD_ZERO, False, A.ACT_NONE, False)
+                    fl = 2.0 * n * sub.shape[2] * sub.shape[3] * cout * (1 + a) * (1 + b_) * c1
+                    done = []
+
+                    def launch(sub=sub, wt=wt, dd=dd):
+                        if A.try_call("segsde_conv2d_fwd_tc", C.byref(ops.view(dz)), None, A.ptr(wt), None,
+                                      C.byref(ops.view(sub)), C.byref(dd), st):
+                            done.append(1)
+                            ops.log_route("dgrad", True)
+                    ops._timed("dgrad", fl, launch, ctx.desc + " phase%d%d" % (a, b_))
+                    ok = ok and bool(done)
+            if ok:
+                phase_dx1 = gx
+            need1 = need1 and not ok           # a refused phase: fall back to the zero-stuffed form below
         if stride == 2 and tc_ch and mode_e == A.PAD_ZERO and not up_e and not nchw and (need1 or need2 or needw):
-            # zero-stuff dz onto the stride-1 output grid: dgrad and wgrad become stride-1 problems
-            hs = x1e.shape[2] + 2 * pad_e - dil * (kh - 1)
-            ws = x1e.shape[3] + 2 * pad_e - dil * (kw - 1)
             dz_s, d_s = dz, ops._desc(kh, kw, 2, pad_e, dil, mode_e, up_e, A.ACT_NONE, nchw)
-            dzu = ops.cl_empty(n, cout, hs, ws, dev, zero=True)
-            A.call("segsde_copy_nhwc", C.byref(ops.view(dz)), C.byref(ops.view(dzu[:, :, ::2, ::2][:, :, :ho, :wo])), st)
-            dz, stride, flops_scale = dzu, 1, 0.25        # algorithmic flops stay those of the strided conv
+            if need1 or need2:
+                # zero-stuff dz onto the stride-1 output grid: dgrad (and a wgrad the strided form refuses) become
+                # stride-1 problems
+                hs = x1e.shape[2] + 2 * pad_e - dil * (kh - 1)
+                ws = x1e.shape[3] + 2 * pad_e - dil * (kw - 1)
+                dzu = ops.cl_empty(n, cout, hs, ws, dev, zero=True)
+                A.call("segsde_copy_nhwc", C.byref(ops.view(dz)), C.byref(ops.view(dzu[:, :, ::2, ::2][:, :, :ho, :wo])), st)
+                dz, stride, flops_scale = dzu, 1, 0.25        # algorithmic flops stay those of the strided conv
         nz, _, hz, wz = dz.shape
         d = ops._desc(kh, kw, stride, pad_e, dil, mode_e, up_e, A.ACT_NONE, nchw)
         dx1 = dx2 = dw = None
@@ -210,6 +247,8 @@ class _Conv2dFn(torch.autograd.Function):
                 A.call("segsde_conv2d_wgrad", C.byref(v1), ops._ref(v2), C.byref(vdz), A.ptr(dw), None, C.byref(d), st)
                 ops.log_route("wgrad", False)
             ops._timed("wgrad", flops_scale * 2.0 * nz * hz * wz * cout * kh * kw * ctot, launch_w, ctx.desc)
+        if phase_dx1 is not None:
+            dx1 = phase_dx1
         return dx1, dx2, dw, db, None, None, None, None, None, None, None, None
 
 

@@ -64,6 +64,22 @@ __global__ void weight_tflip_kernel(const float* __restrict__ w, float* __restri
   wt[idx] = w[(((long long)co * kh + (kh - 1 - r)) * kw + (kw - 1 - s)) * Ctot + c0 + ci];
 }
 
+// Phase (a, b) of the dgrad of a 3x3 / stride-2 / pad-1 convolution: dx[2i+a, 2j+b] is a (1+a) x (1+b)-tap stride-1
+// convolution of dy — row taps: a = 0 -> {w[1] at offset 0}; a = 1 -> {w[2] at offset 0, w[0] at offset +1}, columns alike —
+// instead of a 9-tap convolution over the zero-stuffed dy (4x the MACs).  wt[ci - c0][th][tw][co] = w[co][r(a,th)][s(b,tw)][ci].
+__global__ void weight_phase_s2_kernel(const float* __restrict__ w, float* __restrict__ wt, int Cout, int Ctot, int c0, int cn,
+                                       int a, int b) {
+  const int nth = 1 + a, ntw = 1 + b;
+  const long long total = (long long)cn * nth * ntw * Cout;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int co = (int)(idx % Cout); long long q = idx / Cout;
+  const int tw = (int)(q % ntw); q /= ntw;
+  const int th = (int)(q % nth); const int ci = (int)(q / nth);
+  const int r = a == 0 ? 1 : (th == 0 ? 2 : 0), s = b == 0 ? 1 : (tw == 0 ? 2 : 0);
+  wt[idx] = w[(((long long)co * 3 + r) * 3 + s) * Ctot + c0 + ci];
+}
+
 // dz = dy * act'(y) ; dbias[c] += sum dz   (block = 32 channels x 8 pixel lanes, like the BN reductions)
 __global__ void __launch_bounds__(256) act_bwd_bias_kernel(View y, View dy, View dz, int act, float* __restrict__ dbias,
                                                            long long slab) {
@@ -119,6 +135,14 @@ extern "C" int segsde_weight_transpose_flip(const float* w, float* wt, int cout,
   if (!w || !wt || cout < 1 || kh < 1 || kw < 1 || c_begin < 0 || c_count < 1 || c_begin + c_count > ctot) return SEGSDE_E_ARG;
   const long long total = (long long)c_count * kh * kw * cout;
   weight_tflip_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(w, wt, cout, kh, kw, ctot, c_begin, c_count);
+  return launched();
+}
+extern "C" int segsde_weight_phase_s2(const float* w, float* wt, int cout, int ctot, int c_begin, int c_count, int a, int b,
+                                     void* stream) {
+  if (!w || !wt || cout < 1 || c_begin < 0 || c_count < 1 || c_begin + c_count > ctot || a < 0 || a > 1 || b < 0 || b > 1)
+    return SEGSDE_E_ARG;
+  const long long total = (long long)c_count * (1 + a) * (1 + b) * cout;
+  weight_phase_s2_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(w, wt, cout, ctot, c_begin, c_count, a, b);
   return launched();
 }
 extern "C" int segsde_act_bwd_bias(const segsde_nhwc_t* y, const segsde_nhwc_t* dy, const segsde_nhwc_t* dz, int act,

@@ -1063,9 +1063,16 @@ extern "C" int segsde_conv2d_fwd_tc_stats(const segsde_nhwc_t* x1, const segsde_
   if (v2.p && (v2.h != v1.h || v2.w != v1.w || v2.n != v1.n)) return SEGSDE_E_ARG;
   const int stride_w = d->stride_w ? d->stride_w : d->stride;
   if (stride_w != 1 && stride_w != 2) return SEGSDE_E_UNSUPPORTED;
-  const int Ho = (v1.h + 2 * d->pad - d->dil * (d->kh - 1) - 1) / d->stride + 1;
-  const int Wo = (v1.w + 2 * d->pad - d->dil * (d->kw - 1) - 1) / stride_w + 1;
-  if (vy.h != Ho || vy.w != Wo || vy.n != v1.n) return SEGSDE_E_ARG;
+  int Ho = (v1.h + 2 * d->pad - d->dil * (d->kh - 1) - 1) / d->stride + 1;
+  int Wo = (v1.w + 2 * d->pad - d->dil * (d->kw - 1) - 1) / stride_w + 1;
+  // An output that is up to dil*(k-1) rows / columns LARGER than the formula asks for implicit extra zero padding at
+  // the bottom / right (stride 1 only): the taps that fall outside the input are the TMA out-of-bounds fill.  Used by
+  // the phase decomposition of the stride-2 dgrad (2-tap phases with offsets {0, +1}).
+  if (vy.n != v1.n || vy.h < Ho || vy.w < Wo) return SEGSDE_E_ARG;
+  if (vy.h != Ho || vy.w != Wo) {
+    if (d->stride != 1 || stride_w != 1 || vy.h > Ho + d->dil * (d->kh - 1) || vy.w > Wo + d->dil * (d->kw - 1)) return SEGSDE_E_ARG;
+    Ho = vy.h; Wo = vy.w;
+  }
   if (!vec4_ok(vy)) return SEGSDE_E_UNSUPPORTED;
   const int BN = (Cout % 128 == 0) ? 128 : (Cout % 64 == 0 ? 64 : 32);
   TcConvP p;

@@ -107,6 +107,11 @@ int segsde_pad_prep(const segsde_nhwc_t* x, const segsde_nhwc_t* y, int up, int 
 int segsde_pad_fold(const segsde_nhwc_t* dyp, const segsde_nhwc_t* dx, int up, int pad, void* stream);
 int segsde_weight_transpose_flip(const float* w, float* wt, int cout, int kh, int kw, int ctot, int c_begin,
                                  int c_count, void* stream);
+/* Weights of phase (a, b) in {0,1}^2 of the dgrad of a 3x3 / stride-2 / pad-1 convolution as a (1+a) x (1+b)-tap stride-1
+ * convolution of dy that writes dx[:, a::2, b::2]: wt[ci][th][tw][co] = w[co][r][s][c_begin + ci] with row taps
+ * a=0: {r=1}; a=1: {r=2 (offset 0), r=0 (offset +1)} and columns alike.  w: [cout][3][3][ctot] (OHWI). */
+int segsde_weight_phase_s2(const float* w, float* wt, int cout, int ctot, int c_begin, int c_count, int a, int b,
+                           void* stream);
 int segsde_act_bwd_bias(const segsde_nhwc_t* y, const segsde_nhwc_t* dy, const segsde_nhwc_t* dz, int act,
                         float* dbias, void* stream);
 /* Stem as a GEMM: cols[n,oh,ow,(r*kw+s)*C + c] = (x[n,c,oh*stride-pad+r,ow*stride-pad+s]-0.45)/0.225, zero outside

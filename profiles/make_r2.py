@@ -1,0 +1,94 @@
+"""Builds the committed round-2 summaries from raw captures under gpurun_out/ (scratch):
+  python profiles/make_r2.py curve   gpurun_out/curve_dec5_100steps.json         > profiles/r2_loss_curve.md
+  python profiles/make_r2.py step    gpurun_out/r2_profile_step.log              > profiles/r2_step_profile.md
+  python profiles/make_r2.py dram    gpurun_out/r2_dram.csv <steps-in-capture>   > profiles/r2_ncu_traffic.json   (+ .md on stderr)
+"""
+import collections
+import csv
+import json
+import re
+import sys
+
+
+def curve(path):
+    d = json.load(open(path))
+    a = d["ref_fp32"]
+    names = [("ref_fp32_bit_perturbed", "reference, initial weights perturbed by 1 ulp"),
+             ("ref_cudnn_tf32", "reference, cuDNN TF32 convolutions (its default)"),
+             ("own_fp32_route", "this repo, fp32 CUDA-core route"),
+             ("own_tcgen05_tf32_route", "this repo, tcgen05 TF32 route")]
+    print("# Round 2 — 100-step loss curve through the reference's own `Trainer.train_step` (dec5 recipe)\n")
+    print("Source: `tests/test_gpu_dropin_trainer.py::test_loss_curve_100_steps` on one B200 (ResNet-50 frozen, Adam 1e-4, 64x128,")
+    print("batch 2, 8 synthetic batches cycled, CPU RNG re-seeded per step, dropout masks of the reference run replayed).")
+    print("Deviation = |curve - reference fp32 curve| / initial loss (%.4f).\n" % a[0])
+    print("| curve | step 0 | max over steps 0-7 | mean over 100 steps | max |")
+    print("|---|---:|---:|---:|---:|")
+    for k, label in names:
+        dev = [abs(x - y) / a[0] for x, y in zip(d[k], a)]
+        print("| %s | %.2e | %.2e | %.2e | %.2e |" % (label, dev[0], max(dev[:8]), sum(dev) / len(dev), max(dev)))
+    print("\nReading: the drop-in tracks the reference to 6e-7 at step 0 and stays within 1e-3 for the first 8 optimizer steps;")
+    print("after that every curve — including the reference re-run with its own weights perturbed in the last bit — leaves the")
+    print("fp32 reference curve by > 1e-2 within ~12 steps and by O(0.1-0.4) of the initial loss later: the recipe (random")
+    print("init, train-mode BatchNorm at batch 2, lr 1e-4) amplifies rounding noise ~3x per step.  The tcgen05 TF32 route starts")
+    print("closer to the fp32 curve than the reference's own cuDNN-TF32 run (1.8e-4 vs 7.4e-3 at step 0) — partly because at")
+    print("64x128 the layers narrower than 8 pixels are outside the tensor-core family and run on the fp32 kernels.\n")
+    print("| step | reference fp32 | reference 1-ulp | reference cuDNN TF32 | this repo fp32 route | this repo tcgen05 route |")
+    print("|---:|---:|---:|---:|---:|---:|")
+    for i in list(range(0, 16)) + list(range(16, 100, 6)) + [99]:
+        print("| %d | %.6f | %.6f | %.6f | %.6f | %.6f |" % (i, a[i], d["ref_fp32_bit_perturbed"][i], d["ref_cudnn_tf32"][i],
+                                                         d["own_fp32_route"][i], d["own_tcgen05_tf32_route"][i]))
+
+
+def step(path):
+    txt = open(path).read()
+    print("# Round 2 — one profiled training step (dec5, B=12, 512x1024, 1xB200): CUDA events around every entry point\n")
+    print("Command: `python scratch/profile_step.py` (event pairs add ~5 ms to the step; compare shares).\n")
+    print("```")
+    print(txt.strip())
+    print("```")
+
+
+def dram(path, steps):
+    rows = list(csv.reader(open(path)))
+    hi = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
+    hdr, body = rows[hi], rows[hi + 2:]
+    ki, mi, vi = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value")
+    agg = collections.defaultdict(lambda: collections.defaultdict(float))
+    cnt = collections.Counter()
+    for r in body:
+        if len(r) <= vi:
+            continue
+        name = re.sub(r"^void ", "", re.sub(r"\(.*", "", r[ki]))
+        unit = hdr.index("Metric Unit")
+        v = float(r[vi].replace(",", ""))
+        u = r[unit]
+        if "byte" in u.lower():
+            v *= {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+        agg[name][r[mi]] += v
+        if r[mi] == "gpu__time_duration.sum":
+            cnt[name] += 1
+    steps = float(steps)
+    conv = sum(v["dram__bytes_read.sum"] + v["dram__bytes_write.sum"] for k, v in agg.items() if "tc_conv" in k or "tc_wgrad" in k)
+    rp = [v for k, v in agg.items() if "reproj_march" in k]
+    out = {"conv_family_dram_bytes_per_step": conv / steps,
+           "conv_family_source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum over all tc_conv* / tc_wgrad* launches of "
+                                 "%d bench steps (profiles/r2_dram_by_kernel.md)" % steps}
+    if rp:
+        n = sum(c for k, c in cnt.items() if "reproj_march" in k)
+        out["reproj_dram_bytes_per_launch"] = sum(v["dram__bytes_read.sum"] + v["dram__bytes_write.sum"] for v in rp) / max(n, 1)
+        out["reproj_source"] = "same capture, reproj_march_kernel<true,2>, mean of %d launches" % n
+    print(json.dumps(out, indent=1))
+    sys.stderr.write("# Round 2 — DRAM traffic by kernel, %d bench steps (dec5, B=12), ncu dram__bytes_{read,write}.sum\n\n" % steps)
+    sys.stderr.write("| kernel | launches | time ms | dram read GB | dram write GB | GB/s |\n|---|---:|---:|---:|---:|---:|\n")
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["gpu__time_duration.sum"]):
+        t = v["gpu__time_duration.sum"]
+        tt = t / 1e6 if t > 1e4 else t          # ns -> ms when reported in ns
+        gb = (v["dram__bytes_read.sum"] + v["dram__bytes_write.sum"]) / 1e9
+        if gb < 0.01:
+            continue
+        sys.stderr.write("| `%s` | %d | %.2f | %.2f | %.2f | %.0f |\n" % (k, cnt[k], tt, v["dram__bytes_read.sum"] / 1e9,
+                                                                       v["dram__bytes_write.sum"] / 1e9, gb / (tt * 1e-3 + 1e-12)))
+
+
+if __name__ == "__main__":
+    {"curve": curve, "step": step, "dram": dram}[sys.argv[1]](*sys.argv[2:])

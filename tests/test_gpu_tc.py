@@ -135,7 +135,8 @@ def test_tc_conv_fwd_bwd(ci):
     assert A.launch_count() > n0
 
 
-@pytest.mark.parametrize("k,cin,cout,H,W", [(3, 64, 128, 32, 64), (1, 64, 128, 32, 64), (3, 128, 256, 18, 36), (1, 256, 512, 16, 32)])
+@pytest.mark.parametrize("k,cin,cout,H,W", [(3, 64, 128, 32, 64), (1, 64, 128, 32, 64), (3, 128, 256, 18, 36), (1, 256, 512, 16, 32),
+                                            (3, 64, 64, 17, 35)])
 def test_tc_conv_stride2(k, cin, cout, H, W):
     """ResNet stride-2 convolutions: 3x3 through TMA element strides (fprop) + zero-stuffed dy (dgrad/wgrad),
     1x1 through the ::2 strided view."""
@@ -157,8 +158,10 @@ def test_tc_conv_stride2(k, cin, cout, H, W):
     torch.cuda.synchronize()
     routes = [r for _, r in ops.ROUTES]
     ops.PROFILE, ops.PROFILE_DESC, ops.ROUTES = None, None, None
-    # fprop and dgrad on the tensor cores; wgrad too when the output width is a multiple of its 32-pixel GEMM-K boxes
-    assert routes == ["tc:conv", "tc:conv", "tc:wgrad" if (W // 2) % 32 == 0 else "generic"], routes
+    # fprop and dgrad on the tensor cores (3x3: dgrad = four phase convolutions of 1, 2, 2 and 4 taps; 1x1: the ::2 view);
+    # wgrad too when the output width is a multiple of its 32-pixel GEMM-K boxes
+    n_dgrad = 4 if k == 3 else 1
+    assert routes == ["tc:conv"] + ["tc:conv"] * n_dgrad + ["tc:wgrad" if (W // 2) % 32 == 0 else "generic"], routes
     assert gy.shape == y.shape
     assert rel_err(gy, y) < TOL, "fprop"
     assert rel_err(gx.grad, x.grad) < TOL, "dgrad"

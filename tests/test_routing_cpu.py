@@ -83,15 +83,32 @@ def test_decoder_block_with_upsampled_skip(rec):
     assert w.grad.stride() == w.stride() and b.grad.shape == (128,)
 
 
-def test_stride2_3x3_backward_rewrites(rec):
-    """3x3 / stride 2 (ResNet downsampling blocks): forward strided through the TMA map; backward: dgrad on the
-    zero-stuffed dy as a stride-1 problem, wgrad directly on the strided dy."""
-    from improving_segmentation_with_selfsupervised_depth_b200 import ops
+def test_stride2_3x3_backward_rewrites(rec, monkeypatch):
+    """3x3 / stride 2 (ResNet downsampling blocks): forward strided through the TMA map; backward: dgrad as four phase
+    convolutions (1, 2, 2, 4 taps) of dy writing the (row, column)-parity sub-grids of dx, wgrad directly on the strided
+    dy.  With SEGSDE_PHASE_DGRAD off: dgrad on the zero-stuffed dy as a stride-1 problem (round 1's form)."""
+    from improving_segmentation_with_selfsupervised_depth_b200 import conv_op, ops
     x, w = cl(2, 64, 16, 32), cl(128, 64, 3, 3)
     y = ops.conv2d(x, w, None, stride=2, pad=1)
     assert tuple(y.shape) == (2, 128, 8, 16) and rec.names() == ["segsde_conv2d_fwd_tc"]
     assert struct(rec.args_of("segsde_conv2d_fwd_tc")[5]).stride == 2
     rec.clear()
+    y.backward(torch.ones_like(y), retain_graph=True)
+    n = rec.names()
+    assert n == ["segsde_weight_phase_s2", "segsde_conv2d_fwd_tc"] * 4 + ["segsde_conv2d_wgrad_tc"]
+    taps, subgrids = [], []
+    for call in rec.calls:
+        if call[0] == "segsde_conv2d_fwd_tc":
+            d, out, src = struct(call[1][5]), struct(call[1][4]), struct(call[1][0])
+            taps.append((d.kh, d.kw, d.stride, d.pad))
+            subgrids.append((out.h, out.w, out.sh, out.sw))
+            assert (src.h, src.w, src.c) == (8, 16, 128)                                        # the dense dy
+    assert taps == [(1, 1, 1, 0), (1, 2, 1, 0), (2, 1, 1, 0), (2, 2, 1, 0)]
+    assert subgrids == [(8, 16, 2 * 32 * 64, 2 * 64)] * 4                                       # [:, a::2, b::2] of dx
+    wg = rec.args_of("segsde_conv2d_wgrad_tc")
+    assert (struct(wg[2]).h, struct(wg[2]).w, struct(wg[5]).stride) == (8, 16, 2)                # the dense strided dy
+    rec.clear()
+    monkeypatch.setattr(conv_op, "PHASE_DGRAD_S2", False)
     y.backward(torch.ones_like(y))
     n = rec.names()
     assert n == ["segsde_copy_nhwc", "segsde_weight_transpose_flip", "segsde_conv2d_fwd_tc", "segsde_conv2d_wgrad_tc"]
@@ -99,8 +116,6 @@ def test_stride2_3x3_backward_rewrites(rec):
     assert (stuffed.h, stuffed.w) == (8, 16) and stuffed.sw == 2 * 128 and stuffed.sh == 2 * 32 * 128   # ::2 view of 16x32
     dg_in, dg = struct(rec.args_of("segsde_conv2d_fwd_tc")[0]), struct(rec.args_of("segsde_conv2d_fwd_tc")[5])
     assert (dg_in.h, dg_in.w, dg.stride, dg.pad) == (16, 32, 1, 1)
-    wg = rec.args_of("segsde_conv2d_wgrad_tc")
-    assert (struct(wg[2]).h, struct(wg[2]).w, struct(wg[5]).stride) == (8, 16, 2)                # the dense strided dy
 
 
 def test_1x1_stride2_runs_on_the_subsampled_view(rec):
