@@ -203,9 +203,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s, %dx%d 3-frame, batch %d/GPU (CPU sample: batch %d — host RAM and a bounded run time "
-                               "do not allow batch %d on the CPU)" % (WORKLOAD[args.config], H, W, args.batch, B, args.batch),
-                   "name": args.config},
+        "config": {"workload": "%s, %dx%d 3-frame, batch %d/GPU" % (WORKLOAD[args.config], H, W, args.batch),
+                   "name": args.config, "global_batch": args.batch * args.gpus, "parallelism": "dp%d" % args.gpus,
+                   "cpu_sample": "batch %d per step (a bounded run time does not allow batch %d on the host cores); "
+                                 "images/s = batch / step time" % (B, args.batch)},
         "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -221,6 +222,10 @@ def run_torch_gpu(args):
     import torch
     torch.cuda.set_device(0)
     B, H, W = args.batch, args.height, args.width
+    note = None
+    if args.config == "depthmix" and B != 2:
+        # the reference's own DepthMix mask asserts batch_size == 2 (train.py:586); BASELINE.json's batch 4 cannot run there
+        B, note = 2, "reference asserts batch_size == 2 for mix_mask depthcomp (train.py:586): measured at batch 2"
     step, kind = reference_trainer(args.config, B, H, W)
     for _ in range(max(args.warmup, 3)):
         step()
@@ -243,7 +248,7 @@ def run_torch_gpu(args):
         "vs_baseline": None, "dtype": "tf32 (cuDNN default)", "data": "synthetic",
         "config": {"workload": "%s, %dx%d 3-frame, batch %d/GPU" % (WORKLOAD[args.config], H, W, B), "name": args.config,
                    "code": "unmodified reference Trainer.train_step (oracle/_ref)" if kind == "reference" else "oracle port"},
-        "clocks": clk, "loss": float(last),
+        "clocks": clk, "loss": float(last), "note": note,
         "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
     }))
 
@@ -532,9 +537,10 @@ def run_b200(args):
         "ms_per_step_instrumented": ms_prof / args.steps,
         "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
     }
-    print(json.dumps(out))
-    if world > 1:
+    if world > 1:           # tear NCCL down first: with NCCL_DEBUG set its lines go to stdout, the JSON line stays the last one
         dist.destroy_process_group()
+    sys.stdout.flush()
+    print(json.dumps(out), flush=True)
 
 
 if __name__ == "__main__":

@@ -90,5 +90,45 @@ def dram(path, steps):
                                                                        v["dram__bytes_write.sum"] / 1e9, gb / (tt * 1e-3 + 1e-12)))
 
 
+def reproj(rep, label="", ms_events=""):
+    """ncu --set full capture of reproj_march_kernel<true,2>: headline counters + executed-instruction opcode census."""
+    import subprocess
+    raw = list(csv.reader(subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout.splitlines()))
+    hdr, vals, units = raw[0], raw[2], raw[1]
+    want = ["gpu__time_duration.sum", "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+            "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
+            "launch__shared_mem_per_block_dynamic", "dram__bytes_read.sum", "dram__bytes_write.sum",
+            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+            "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+            "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "smsp__warps_eligible.avg.per_cycle_active"]
+    print("# Round 2 — `reproj_march_kernel<true, 2>` (fused reprojection loss, all 4 scales + identity sweep, gradients on)\n")
+    print("Capture: `ncu --set full --clock-control none --import-source on -k regex:reproj_march -s 2 -c 1 python scratch/reproj_only.py`")
+    print("(B=12, 512x1024, one B200)%s.  CUDA-event time of the same launch outside the profiler: %s.\n" % (label and " — " + label, ms_events))
+    print("| metric | value |\n|---|---:|")
+    got = {}
+    for w in want:
+        if w in hdr:
+            i = hdr.index(w)
+            got[w] = vals[i]
+            print("| `%s` | %s %s |" % (w, vals[i], units[i]))
+    src = list(csv.reader(subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout.splitlines()))
+    h2 = src[1]
+    ia, isrc, ist = h2.index("Instructions Executed"), h2.index("Source"), h2.index("Warp Stall Sampling (All Samples)")
+    c, st = collections.Counter(), collections.Counter()
+    for r in src[2:]:
+        ops_ = [o for o in r[isrc].split() if not o.startswith("@")]
+        name = ops_[0].split(".")[0] if ops_ else "?"
+        c[name] += int(r[ia])
+        st[name] += int(r[ist])
+    tot, stt = sum(c.values()), sum(st.values()) or 1
+    warps = float(got.get("launch__grid_size", "7104").replace(",", ""))
+    steps = warps * (4 * 36 + 36)
+    print("\nExecuted warp-instructions: %.3g total = %.0f per warp row-step (7104 warps x (4 scale sweeps + identity sweep) x 36 rows)." % (tot, tot / steps))
+    print("Algorithmic bytes 293.3 MB (target + 2 sources once, 4 disparity maps read, 4 gradients written).\n")
+    print("| opcode | share of executed instr | share of stall samples |\n|---|---:|---:|")
+    for k, v in c.most_common(16):
+        print("| %s | %.1f %% | %.1f %% |" % (k, 100.0 * v / tot, 100.0 * st[k] / stt))
+
+
 if __name__ == "__main__":
-    {"curve": curve, "step": step, "dram": dram}[sys.argv[1]](*sys.argv[2:])
+    {"curve": curve, "step": step, "dram": dram, "reproj": reproj}[sys.argv[1]](*sys.argv[2:])
