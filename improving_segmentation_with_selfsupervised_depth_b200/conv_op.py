@@ -27,6 +27,11 @@ TC_STRIDE2_FPROP = True      # 3x3/s2 forward on the tensor cores via TMA elemen
 PHASE_DGRAD_S2 = os.environ.get("SEGSDE_PHASE_DGRAD", "1") != "0"
 
 
+# nearest x2 upsample + reflect pad + 3x3 conv (no skip) as four 2x2 phase convolutions on the low-res input
+# (SEGSDE_PHASE_UPCONV=0 restores the materialised form)
+PHASE_UPCONV = os.environ.get("SEGSDE_PHASE_UPCONV", "1") != "0"
+
+
 def _tc_enabled():
     return ops.USE_TC and A.lib().segsde_tc_available() == 1
 
@@ -252,6 +257,96 @@ class _Conv2dFn(torch.autograd.Function):
         return dx1, dx2, dw, db, None, None, None, None, None, None, None, None
 
 
+class _UpConv3x3Fn(torch.autograd.Function):
+    """y = act(conv3x3(reflect_pad1(nearest_up2(x))) + bias) — the decoder's `upconv(i,1)` without a skip connection
+    (depth_decoder.py:93-101 at the finest stage) — as FOUR 2x2 "phase" convolutions on the replicate-padded low-res
+    input (csrc/conv_aux.cu: output pixel (2i+a, 2j+b) sees the low-res rows {i-1,i,i} or {i,i,i+1}): 9/4 of the MACs in
+    fprop, dgrad and wgrad, and neither the upsampled + padded copy (4x the low-res bytes) nor its gradient exist."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act):
+        A.require_cuda(x, weight)
+        x = ops.as_cl(x)
+        w = ops.ohwi(weight.detach())
+        cout, c1 = w.shape[0], w.shape[1]
+        n, _, h, wd = x.shape
+        dev, st = x.device, A.stream_ptr()
+        xp = ops.cl_empty(n, c1, h + 2, wd + 2, dev)
+        A.call("segsde_pad_replicate", C.byref(ops.view(x)), C.byref(ops.view(xp)), st)
+        y = ops.cl_empty(n, cout, 2 * h, 2 * wd, dev)
+        b = bias.detach() if bias is not None else None
+        d22 = ops._desc(2, 2, 1, 0, 1, A.PAD_ZERO, False, act, False)
+        desc = "%d->%d k3 up2 out %dx%d phases" % (c1, cout, 2 * h, 2 * wd)
+        for a in (0, 1):
+            for b_ in (0, 1):
+                wp = torch.empty(cout * 4 * c1, device=dev, dtype=torch.float32)
+                A.call("segsde_weight_phase_up", A.ptr(w), A.ptr(wp), C.c_int(cout), C.c_int(c1), C.c_int(0), C.c_int(c1),
+                       C.c_int(a), C.c_int(b_), st)
+                _fwd(xp[:, :, a:a + h + 1, b_:b_ + wd + 1], None, wp, b, y[:, :, a::2, b_::2], d22, "fprop",
+                     2.0 * n * h * wd * cout * 9 * c1, desc)
+        ctx.save_for_backward(xp, w, y if act != A.ACT_NONE else None)
+        ctx.cfg = (act, bias is not None, desc)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xp, w, y = ctx.saved_tensors
+        act, has_bias, desc = ctx.cfg
+        cout, c1 = w.shape[0], w.shape[1]
+        n, _, hp, wp_ = xp.shape
+        h, wd = hp - 2, wp_ - 2
+        dev, st = dy.device, A.stream_ptr()
+        dy = ops.as_cl(dy)
+        need_x, need_w, need_b = ctx.needs_input_grad[:3]
+        db = ops.zeros_f32(cout, dev) if (has_bias and need_b) else None
+        dz = dy
+        if act != A.ACT_NONE or db is not None:
+            dzb = ops.cl_empty(*dy.shape, dev) if act != A.ACT_NONE else None
+            A.call("segsde_act_bwd_bias", ops._ref(ops.view(y)) if y is not None else None, C.byref(ops.view(dy)),
+                   ops._ref(ops.view(dzb)) if dzb is not None else None, C.c_int(act), A.ptr(db), st)
+            dz = dy if dzb is None else dzb
+        fl = 2.0 * n * h * wd * cout * 9 * c1            # one phase's share of the algorithmic FLOPs of the 3x3 convolution
+        dx = dw = None
+        wps = {}
+        for a in (0, 1):
+            for b_ in (0, 1):
+                wp = torch.empty(cout * 4 * c1, device=dev, dtype=torch.float32)
+                A.call("segsde_weight_phase_up", A.ptr(w), A.ptr(wp), C.c_int(cout), C.c_int(c1), C.c_int(0), C.c_int(c1),
+                       C.c_int(a), C.c_int(b_), st)
+                wps[(a, b_)] = wp
+        if need_x:
+            gs = []
+            dd = ops._desc(2, 2, 1, 1, 1, A.PAD_ZERO, False, A.ACT_NONE, False)
+            for a in (0, 1):
+                for b_ in (0, 1):
+                    wt = torch.empty(c1 * 4 * cout, device=dev, dtype=torch.float32)
+                    A.call("segsde_weight_transpose_flip", A.ptr(wps[(a, b_)]), A.ptr(wt), C.c_int(cout), C.c_int(2), C.c_int(2),
+                           C.c_int(c1), C.c_int(0), C.c_int(c1), st)
+                    g = ops.cl_empty(n, c1, h + 1, wd + 1, dev)
+                    _fwd(dz[:, :, a::2, b_::2], None, wt, None, g, dd, "dgrad", fl, desc)
+                    gs.append(g)
+            dx = ops.cl_empty(n, c1, h, wd, dev)
+            A.call("segsde_phase_up_fold", A.ptr(gs[0]), A.ptr(gs[1]), A.ptr(gs[2]), A.ptr(gs[3]), C.byref(ops.view(dx)), st)
+        if need_w:
+            dwp = ops.zeros_f32(4 * cout * 4 * c1, dev)
+            d22 = ops._desc(2, 2, 1, 0, 1, A.PAD_ZERO, False, A.ACT_NONE, False)
+            for a in (0, 1):
+                for b_ in (0, 1):
+                    part = dwp[(a * 2 + b_) * cout * 4 * c1:(a * 2 + b_ + 1) * cout * 4 * c1]
+                    v1, vdz = ops.view(xp[:, :, a:a + h + 1, b_:b_ + wd + 1]), ops.view(dz[:, :, a::2, b_::2])
+
+                    def launch_w(v1=v1, vdz=vdz, part=part):
+                        if _tc_enabled() and A.try_call("segsde_conv2d_wgrad_tc", C.byref(v1), None, C.byref(vdz), A.ptr(part),
+                                                        None, C.byref(d22), st):
+                            return ops.log_route("wgrad", True)
+                        A.call("segsde_conv2d_wgrad", C.byref(v1), None, C.byref(vdz), A.ptr(part), None, C.byref(d22), st)
+                        ops.log_route("wgrad", False)
+                    ops._timed("wgrad", fl, launch_w, desc)
+            dw = ops.zeros_like_w(w)
+            A.call("segsde_weight_phase_up_fold", A.ptr(dwp), A.ptr(dw), C.c_int(cout), C.c_int(c1), C.c_int(0), C.c_int(c1), st)
+        return dx, dw, db, None
+
+
 def _band_view(xp, n, hp, wo, wp, P):
     """The overlapping row-band view of a segsde_stem_pack buffer: pixel (y, ox) exposes the 8*P contiguous floats
     that start at padded pixel (y, 2*ox) — c = 8*P, horizontal stride 2*P floats (include/segsde_b200.h)."""
@@ -447,6 +542,10 @@ def conv2d(x1, weight, bias=None, x2=None, stride=1, pad=0, dil=1, pad_mode=A.PA
         if not box[1]:
             A.call("segsde_bn_stats", C.byref(ops.view(y.detach())), A.ptr(bn_stats), A.stream_ptr())
         return y
+    if (PHASE_UPCONV and up1 and x2 is None and tuple(weight.shape[2:]) == (3, 3) and stride == 1 and pad == 1 and dil == 1
+            and pad_mode == A.PAD_REFLECT and not nchw_norm_in and bn_stats is None and weight.shape[1] % 64 == 0
+            and weight.shape[0] % 64 == 0 and x1.shape[-1] % 32 == 0 and x1.shape[-2] >= 2 and _tc_enabled()):
+        return _UpConv3x3Fn.apply(x1, weight, bias, act)
     if (weight.shape[0] == 1 and tuple(weight.shape[2:]) == (3, 3) and x2 is None and not up1 and stride == 1
             and pad == 1 and dil == 1 and not nchw_norm_in and weight.shape[1] % 64 == 0 and x1.shape[-1] % 32 == 0
             and _tc_enabled()):

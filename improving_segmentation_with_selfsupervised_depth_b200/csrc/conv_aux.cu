@@ -64,6 +64,44 @@ __global__ void weight_tflip_kernel(const float* __restrict__ w, float* __restri
   wt[idx] = w[(((long long)co * kh + (kh - 1 - r)) * kw + (kw - 1 - s)) * Ctot + c0 + ci];
 }
 
+// The same pass for FEW channels (the 1-channel disparity heads, the 12-channel pose output): one thread per pixel, the
+// channels in a register loop, block-level reduction of the bias sums.  The 32-channels-per-warp kernel above leaves
+// 31 of 32 lanes idle at C = 1 (ncu, round 2: 0.24 ms per head at 47 GB/s — 1.4 ms of a 57 ms step).
+template <int MAXC>
+__global__ void __launch_bounds__(256) act_bwd_bias_fewc_kernel(View y, View dy, View dz, int act, float* __restrict__ dbias) {
+  const long long P = (long long)dy.n * dy.h * dy.w;
+  const int C = dy.c;
+  float s[MAXC];
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) s[c] = 0.f;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(p % dy.w); const long long q = p / dy.w;
+    const int h = (int)(q % dy.h), n = (int)(q / dy.h);
+    const long long od = dy.off(n, h, w), oy = y.p ? y.off(n, h, w) : 0, oz = dz.p ? dz.off(n, h, w) : 0;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      if (c >= C) break;
+      float g = dy.p[od + c];
+      if (act != SEGSDE_ACT_NONE) g *= act_grad_from_out(y.p[oy + c], act);
+      if (dz.p) dz.p[oz + c] = g;
+      s[c] += g;
+    }
+  }
+  if (!dbias) return;
+  __shared__ float red[8][MAXC];
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    const float v = warp_sum(s[c]);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][c] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    atomicAdd(dbias + threadIdx.x, t);
+  }
+}
+
 // Phase (a, b) of the dgrad of a 3x3 / stride-2 / pad-1 convolution: dx[2i+a, 2j+b] is a (1+a) x (1+b)-tap stride-1
 // convolution of dy — row taps: a = 0 -> {w[1] at offset 0}; a = 1 -> {w[2] at offset 0, w[0] at offset +1}, columns alike —
 // instead of a 9-tap convolution over the zero-stuffed dy (4x the MACs).  wt[ci - c0][th][tw][co] = w[co][r(a,th)][s(b,tw)][ci].
@@ -78,6 +116,100 @@ __global__ void weight_phase_s2_kernel(const float* __restrict__ w, float* __res
   const int th = (int)(q % nth); const int ci = (int)(q / nth);
   const int r = a == 0 ? 1 : (th == 0 ? 2 : 0), s = b == 0 ? 1 : (tw == 0 ? 2 : 0);
   wt[idx] = w[(((long long)co * 3 + r) * 3 + s) * Ctot + c0 + ci];
+}
+
+// ---- nearest x2 upsampling + ReflectionPad2d(1) + 3x3 convolution as four 2x2 "phase" convolutions on the low-res input ----
+// Output pixel (2i+a, 2j+b) sees the upsampled rows 2i+a-1 .. 2i+a+1, i.e. the low-res rows {i-1, i, i} (a = 0) or
+// {i, i, i+1} (a = 1): a 2-tap convolution with pre-summed weights  a=0: {w0, w1+w2},  a=1: {w0+w1, w2}  (columns alike),
+// and the reflection of the UPSAMPLED image at the border is a REPLICATION of the low-res one.  9/4 of the MACs, the
+// upsampled + padded copy (4x the low-res bytes) is never written, its gradient never folded back.
+//
+// xp[n, u, v, c] = x[n, clamp(u - 1), clamp(v - 1), c]   (replicate padding by 1)
+__global__ void pad_replicate_kernel(View x, View y) {
+  const int cq = y.c / 4;
+  const long long total = (long long)y.n * y.h * y.w * cq;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % cq) * 4; long long q = idx / cq;
+  const int v = (int)(q % y.w); q /= y.w;
+  const int u = (int)(q % y.h); const int n = (int)(q / y.h);
+  const int h = min(max(u - 1, 0), x.h - 1), w = min(max(v - 1, 0), x.w - 1);
+  *reinterpret_cast<float4*>(y.p + y.off(n, u, v) + c) = *reinterpret_cast<const float4*>(x.p + x.off(n, h, w) + c);
+}
+// wp[co][dr][ds][ci] = sum_{r in R(a,dr)} sum_{s in R(b,ds)} w[co][r][s][c0 + ci],  R(0,0)={0}, R(0,1)={1,2}, R(1,0)={0,1}, R(1,1)={2}
+__device__ __forceinline__ void phase_taps(int a, int d, int& lo, int& hi) {
+  if (a == 0) { lo = d == 0 ? 0 : 1; hi = d == 0 ? 0 : 2; } else { lo = d == 0 ? 0 : 2; hi = d == 0 ? 1 : 2; }
+}
+__global__ void weight_phase_up_kernel(const float* __restrict__ w, float* __restrict__ wp, int Cout, int Ctot, int c0, int cn,
+                                       int a, int b) {
+  const long long total = (long long)Cout * 4 * cn;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ci = (int)(idx % cn); long long q = idx / cn;
+  const int ds = (int)(q % 2); q /= 2;
+  const int dr = (int)(q % 2); const int co = (int)(q / 2);
+  int r0, r1, s0, s1;
+  phase_taps(a, dr, r0, r1); phase_taps(b, ds, s0, s1);
+  float acc = 0.f;
+  for (int r = r0; r <= r1; ++r)
+    for (int s2 = s0; s2 <= s1; ++s2) acc += w[(((long long)co * 3 + r) * 3 + s2) * Ctot + c0 + ci];
+  wp[idx] = acc;
+}
+// adjoint of the pre-summation: dw[co][r][s][c0+ci] (+)= sum over the phases (a,b) and taps (dr,ds) with r in R(a,dr), s in R(b,ds)
+// of dwp[a][b][co][dr][ds][ci]      (dwp: [2][2][Cout][2][2][cn])
+__global__ void weight_phase_up_fold_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Cout, int Ctot, int c0,
+                                            int cn) {
+  const long long total = (long long)Cout * 9 * cn;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ci = (int)(idx % cn); long long q = idx / cn;
+  const int s = (int)(q % 3); q /= 3;
+  const int r = (int)(q % 3); const int co = (int)(q / 3);
+  float acc = 0.f;
+  for (int a = 0; a < 2; ++a)
+    for (int dr = 0; dr < 2; ++dr) {
+      int r0, r1; phase_taps(a, dr, r0, r1);
+      if (r < r0 || r > r1) continue;
+      for (int b = 0; b < 2; ++b)
+        for (int ds = 0; ds < 2; ++ds) {
+          int s0, s1; phase_taps(b, ds, s0, s1);
+          if (s < s0 || s > s1) continue;
+          acc += dwp[(((((long long)(a * 2 + b) * Cout + co) * 2 + dr) * 2 + ds)) * cn + ci];
+        }
+    }
+  dw[(((long long)co * 3 + r) * 3 + s) * Ctot + c0 + ci] += acc;
+}
+// dx[n,i,j,c] = sum over the replicate preimages (u,v) of (i,j) in xp and the phases (a,b) of g_ab[n, u-a, v-b, c]
+// (g: [2][2] buffers of shape [n, h+1, w+1, c], the gradients w.r.t. the four phase views xp[:, a:a+h+1, b:b+w+1])
+struct PhaseG { const float* p[4]; };
+__global__ void phase_up_fold_kernel(PhaseG g, View dx) {
+  const int cq = dx.c / 4;
+  const long long total = (long long)dx.n * dx.h * dx.w * cq;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % cq) * 4; long long q = idx / cq;
+  const int j = (int)(q % dx.w); q /= dx.w;
+  const int i = (int)(q % dx.h); const int n = (int)(q / dx.h);
+  const int H1 = dx.h + 1, W1 = dx.w + 1;
+  int us[3], vs[3]; int nu = 0, nv = 0;
+  us[nu++] = i + 1; if (i == 0) us[nu++] = 0; if (i == dx.h - 1) us[nu++] = dx.h + 1;
+  vs[nv++] = j + 1; if (j == 0) vs[nv++] = 0; if (j == dx.w - 1) vs[nv++] = dx.w + 1;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int iu = 0; iu < nu; ++iu)
+    for (int iv = 0; iv < nv; ++iv)
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        const int uu = us[iu] - a;
+        if (uu < 0 || uu >= H1) continue;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const int vv = vs[iv] - b;
+          if (vv < 0 || vv >= W1) continue;
+          const float4 t = *reinterpret_cast<const float4*>(g.p[a * 2 + b] + (((long long)n * H1 + uu) * W1 + vv) * dx.c + c);
+          acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        }
+      }
+  *reinterpret_cast<float4*>(dx.p + dx.off(n, i, j) + c) = acc;
 }
 
 // dz = dy * act'(y) ; dbias[c] += sum dz   (block = 32 channels x 8 pixel lanes, like the BN reductions)
@@ -137,6 +269,40 @@ extern "C" int segsde_weight_transpose_flip(const float* w, float* wt, int cout,
   weight_tflip_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(w, wt, cout, kh, kw, ctot, c_begin, c_count);
   return launched();
 }
+extern "C" int segsde_pad_replicate(const segsde_nhwc_t* x, const segsde_nhwc_t* y, void* stream) {
+  if (!x || !y || !x->ptr || !y->ptr) return SEGSDE_E_ARG;
+  View vx = mk(x), vy = mk(y);
+  if (vy.h != vx.h + 2 || vy.w != vx.w + 2 || vy.c != vx.c || vy.n != vx.n) return SEGSDE_E_ARG;
+  if (!vec4_ok(vx) || !vec4_ok(vy)) return SEGSDE_E_ALIGN;
+  const long long total = (long long)vy.n * vy.h * vy.w * (vy.c / 4);
+  pad_replicate_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(vx, vy);
+  return launched();
+}
+extern "C" int segsde_weight_phase_up(const float* w, float* wp, int cout, int ctot, int c_begin, int c_count, int a, int b,
+                                     void* stream) {
+  if (!w || !wp || cout < 1 || c_begin < 0 || c_count < 1 || c_begin + c_count > ctot || a < 0 || a > 1 || b < 0 || b > 1)
+    return SEGSDE_E_ARG;
+  const long long total = (long long)cout * 4 * c_count;
+  weight_phase_up_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(w, wp, cout, ctot, c_begin, c_count, a, b);
+  return launched();
+}
+extern "C" int segsde_weight_phase_up_fold(const float* dwp, float* dw, int cout, int ctot, int c_begin, int c_count,
+                                          void* stream) {
+  if (!dwp || !dw || cout < 1 || c_begin < 0 || c_count < 1 || c_begin + c_count > ctot) return SEGSDE_E_ARG;
+  const long long total = (long long)cout * 9 * c_count;
+  weight_phase_up_fold_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(dwp, dw, cout, ctot, c_begin, c_count);
+  return launched();
+}
+extern "C" int segsde_phase_up_fold(const float* g00, const float* g01, const float* g10, const float* g11,
+                                   const segsde_nhwc_t* dx, void* stream) {
+  if (!g00 || !g01 || !g10 || !g11 || !dx || !dx->ptr) return SEGSDE_E_ARG;
+  View vx = mk(dx);
+  if (!vec4_ok(vx)) return SEGSDE_E_ALIGN;
+  PhaseG g; g.p[0] = g00; g.p[1] = g01; g.p[2] = g10; g.p[3] = g11;
+  const long long total = (long long)vx.n * vx.h * vx.w * (vx.c / 4);
+  phase_up_fold_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(g, vx);
+  return launched();
+}
 extern "C" int segsde_weight_phase_s2(const float* w, float* wt, int cout, int ctot, int c_begin, int c_count, int a, int b,
                                      void* stream) {
   if (!w || !wt || cout < 1 || c_begin < 0 || c_count < 1 || c_begin + c_count > ctot || a < 0 || a > 1 || b < 0 || b > 1)
@@ -154,6 +320,12 @@ extern "C" int segsde_act_bwd_bias(const segsde_nhwc_t* y, const segsde_nhwc_t* 
   if (fast_reduce_ok(vd) && (act == SEGSDE_ACT_NONE || pix_contig(vy)) && (!vz.p || pix_contig(vz)))
     return act_bwd_bias_fast(vy, vd, vz, act, dbias, as_stream(stream));
   const long long P = (long long)vd.n * vd.h * vd.w;
+  if (vd.c <= 16) {
+    long long blocks = cdiv(P, 256 * 4); if (blocks > 148 * 8) blocks = 148 * 8; if (blocks < 1) blocks = 1;
+    if (vd.c <= 4) act_bwd_bias_fewc_kernel<4><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(vy, vd, vz, act, dbias);
+    else act_bwd_bias_fewc_kernel<16><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(vy, vd, vz, act, dbias);
+    return launched();
+  }
   const int groups = cdiv(vd.c, 32);
   long long want = (148LL * 8) / groups; if (want < 1) want = 1;
   long long s = cdiv(P, 64); if (s > want) s = want; if (s < 1) s = 1;

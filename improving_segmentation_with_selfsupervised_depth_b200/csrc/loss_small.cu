@@ -9,8 +9,16 @@ __global__ void smooth_mean_kernel(const float* __restrict__ disp, int hw, float
   // one block per sample; fixed-order reduction (deterministic)
   const int b = blockIdx.x;
   const float* d = disp + (size_t)b * hw;
-  double a = 0.0;
-  for (int i = threadIdx.x; i < hw; i += blockDim.x) a += (double)d[i];
+  // per-thread partial sums in four independent fp32 chains (<= 128 terms each at 512x1024: disparities in (0,1), the
+  // rounding of such a chain is ~1e-6 relative), fp64 only across threads — a dependent chain of fp64 adds per element
+  // ran at 100 GB/s on the B200's reduced fp64 pipe
+  float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
+  int i = threadIdx.x;
+  for (; i + 3 * (int)blockDim.x < hw; i += 4 * blockDim.x) {
+    f0 += d[i]; f1 += d[i + blockDim.x]; f2 += d[i + 2 * blockDim.x]; f3 += d[i + 3 * blockDim.x];
+  }
+  for (; i < hw; i += blockDim.x) f0 += d[i];
+  double a = ((double)f0 + (double)f1) + ((double)f2 + (double)f3);
   __shared__ double sh[32];
   a = warp_sum_d(a);
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;

@@ -107,6 +107,18 @@ int segsde_pad_prep(const segsde_nhwc_t* x, const segsde_nhwc_t* y, int up, int 
 int segsde_pad_fold(const segsde_nhwc_t* dyp, const segsde_nhwc_t* dx, int up, int pad, void* stream);
 int segsde_weight_transpose_flip(const float* w, float* wt, int cout, int kh, int kw, int ctot, int c_begin,
                                  int c_count, void* stream);
+/* nearest x2 upsampling + ReflectionPad2d(1) + 3x3 convolution (monodepth_layers.py:ConvBlock after depth_decoder.py:93-96)
+ * as four 2x2 "phase" convolutions on the replicate-padded LOW-RES input: output pixel (2i+a, 2j+b) = 2x2 taps of
+ * xp[:, a:, b:] with weights pre-summed over the 3x3 taps that fall on the same low-res pixel (a=0: {w0, w1+w2},
+ * a=1: {w0+w1, w2}; columns alike).  pad_replicate: xp [n,h+2,w+2,c] from x.  weight_phase_up: wp[cout][2][2][c_count]
+ * of phase (a,b) from w [cout][3][3][ctot].  weight_phase_up_fold: the adjoint, dw += fold(dwp[2][2][cout][2][2][c_count]).
+ * phase_up_fold: dx [n,h,w,c] from the four gradients g_ab [n,h+1,w+1,c] w.r.t. the phase views (adjoint of the views +
+ * of the replicate padding). */
+int segsde_pad_replicate(const segsde_nhwc_t* x, const segsde_nhwc_t* xp, void* stream);
+int segsde_weight_phase_up(const float* w, float* wp, int cout, int ctot, int c_begin, int c_count, int a, int b, void* stream);
+int segsde_weight_phase_up_fold(const float* dwp, float* dw, int cout, int ctot, int c_begin, int c_count, void* stream);
+int segsde_phase_up_fold(const float* g00, const float* g01, const float* g10, const float* g11, const segsde_nhwc_t* dx,
+                         void* stream);
 /* Weights of phase (a, b) in {0,1}^2 of the dgrad of a 3x3 / stride-2 / pad-1 convolution as a (1+a) x (1+b)-tap stride-1
  * convolution of dy that writes dx[:, a::2, b::2]: wt[ci][th][tw][co] = w[co][r][s][c_begin + ci] with row taps
  * a=0: {r=1}; a=1: {r=2 (offset 0), r=0 (offset +1)} and columns alike.  w: [cout][3][3][ctot] (OHWI). */

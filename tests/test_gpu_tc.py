@@ -50,6 +50,9 @@ CASES = [
     (64, 0, 128, 1, 0, 1, False, False, 0, True, 4, 128, 160),
     (64, 0, 64, 3, 1, 1, False, False, 1, False, 16, 96, 64),
     (64, 64, 128, 1, 0, 1, False, False, 2, True, 5, 127, 144),
+    # nearest x2 upsample + reflect pad + 3x3 WITHOUT a skip: four 2x2 phase convolutions on the low-res input
+    (64, 0, 64, 3, 1, 1, True, True, 2, True, 2, 16, 32),
+    (128, 0, 64, 3, 1, 1, True, True, 0, False, 1, 7, 64),
 ]
 # The kernel every launch of a case must take, in launch order: fprop, dgrad (one entry per source that gets a
 # gradient; two sources outside the family share ONE generic launch), wgrad.  "generic" = the CUDA-core kernels: the
@@ -73,6 +76,8 @@ ROUTE = [
     ["tc:conv256", "tc:conv256", "tc:wgrad"],
     ["tc:conv256", "tc:conv256", "tc:wgrad3x3"],
     ["tc:conv256", "tc:conv256", "tc:conv256", "generic"],  # Wo = 144 is not a multiple of 32
+    ["tc:conv"] * 4 + ["tc:conv"] * 4 + ["tc:wgrad"] * 4,    # fprop, dgrad, wgrad: one launch per phase
+    ["tc:conv"] * 4 + ["tc:conv"] * 4 + ["tc:wgrad"] * 4,
 ]
 
 
