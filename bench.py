@@ -477,10 +477,11 @@ def run_b200(args):
     tot_ms = sum(v[1] for v in fam.values()) or 1.0
     tot_fl = sum(v[0] for v in fam.values())
     notes = {}
-    try:
-        notes = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")))
-    except Exception:
-        pass
+    for fn in ("r2_ncu_traffic.json", "r2_tf32_peak.json"):      # committed ncu DRAM capture; measured TF32 cuBLAS peak
+        try:
+            notes.update(json.load(open(os.path.join(ROOT, "profiles", fn))))
+        except Exception:
+            pass
     roof = {"bound": "tensor", "achieved": tot_fl / (tot_ms * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
             "frac": tot_fl / (tot_ms * 1e-3) / 1e12 / peak_tf, "traffic": notes.get("conv_family_dram_bytes_per_step"),
             "traffic_source": notes.get("conv_family_source"), "peak_source": peak_src,
