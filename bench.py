@@ -57,6 +57,8 @@ def parse():
     ap.add_argument("--ref-batch", type=int, default=2, help="bounded CPU sample: batch of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tc", action="store_true", help="force the generic CUDA-core convolution path")
+    ap.add_argument("--entry-profile", action="store_true",
+                    help="diagnostic: print ms/step per C-ABI entry point of the instrumented pass to stderr")
     a = ap.parse_args()
     if not a.batch:
         a.batch = DEFAULT_BATCH[a.config]
@@ -405,6 +407,8 @@ def run_b200(args):
             # every step
             main = torch.cuda.current_stream()
             uploaded = [torch.cuda.Event(), torch.cuda.Event()]
+            loss_read = [torch.cuda.Event(), torch.cuda.Event()]
+            loss_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
             consumed = [torch.cuda.Event(), torch.cuda.Event()]
 
             def upload(slot, first_use):
@@ -422,7 +426,15 @@ def run_b200(args):
                     upload(slot ^ 1, i == 0)
                 loss_t = step(dev_bufs[slot])
                 consumed[slot].record(main)
-                last = loss_t.item()                # D2H read of the step's loss
+                # D2H read of the step's loss, every step: an async copy into pinned memory, consumed one step late
+                # (the way a training loop logs) so that the host keeps issuing step i+1 while step i runs
+                loss_host[i % 2].copy_(loss_t.detach().reshape(1), non_blocking=True)
+                loss_read[i % 2].record(main)
+                if i > 0:
+                    loss_read[(i - 1) % 2].synchronize()
+                    last = float(loss_host[(i - 1) % 2])
+            loss_read[(nsteps - 1) % 2].synchronize()
+            last = float(loss_host[(nsteps - 1) % 2])
         else:
             for _ in range(nsteps):
                 last = step(resident)
@@ -451,10 +463,21 @@ def run_b200(args):
     # pass 2 (roofline only): every convolution launch and the fused reprojection launch bracketed by CUDA events on
     # the launching stream — the event pairs cost ~1 % of the step, so they stay out of the reported number
     ops.PROFILE = []
-    A.PROFILE, A.PROFILE_NAMES = [], {"segsde_reproj_fused"}
+    A.PROFILE, A.PROFILE_NAMES = [], (None if args.entry_profile else {"segsde_reproj_fused"})
     ms_prof, _ = timed(args.steps, e2e=False)
     prof, ops.PROFILE = ops.PROFILE, None
     rprof, A.PROFILE, A.PROFILE_NAMES = A.PROFILE, None, None
+    if args.entry_profile and rank == 0:          # per-entry-point table of the instrumented pass (stderr)
+        agg = {}
+        for nm, e0, e1 in rprof:
+            a = agg.setdefault(nm, [0.0, 0])
+            a[0] += e0.elapsed_time(e1)
+            a[1] += 1
+        sys.stderr.write("--- %s: ms per step by C-ABI entry point (instrumented pass, %.1f ms/step)\n"
+                         % (args.config, ms_prof / args.steps))
+        for nm, a in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+            sys.stderr.write("%-36s %8.2f ms %6.0f calls\n" % (nm, a[0] / args.steps, a[1] / args.steps))
+    rprof = [r for r in rprof if r[0] == "segsde_reproj_fused"]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

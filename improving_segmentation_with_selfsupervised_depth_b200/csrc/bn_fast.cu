@@ -50,29 +50,58 @@ __global__ void __launch_bounds__(256) colreduce_fast_kernel(Rows x, Rows y, Row
   double d1[4] = {0, 0, 0, 0}, d2[4] = {0, 0, 0, 0};
   float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), a2 = a1;
   int cnt = 0;
-  if (cv) {
-    for (long long p = pbeg + threadIdx.y * ppw + sub; p < pend; p += 8 * ppw) {
-      if (MODE == 0) {
-        const float4 v = ld4(x.p + p * x.ld + c);
-        const float e0 = v.x - sh.x, e1 = v.y - sh.y, e2 = v.z - sh.z, e3 = v.w - sh.w;
-        a1.x += e0; a1.y += e1; a1.z += e2; a1.w += e3;
-        a2.x = fmaf(e0, e0, a2.x); a2.y = fmaf(e1, e1, a2.y); a2.z = fmaf(e2, e2, a2.z); a2.w = fmaf(e3, e3, a2.w);
-      } else if (MODE == 1) {
-        float4 g = ld4(dy.p + p * dy.ld + c);
-        const float4 v = ld4(x.p + p * x.ld + c);
-        if (act == SEGSDE_ACT_RELU) {
-          float4 o;
-          if (y.p) o = ld4(y.p + p * y.ld + c);
-          else {
-            o.x = (v.x - mu.x) * sc.x + bt.x; o.y = (v.y - mu.y) * sc.y + bt.y;
-            o.z = (v.z - mu.z) * sc.z + bt.z; o.w = (v.w - mu.w) * sc.w + bt.w;
-          }
-          g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f; g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
+  // U pixels per trip with every load issued before the first use: the reduction passes are latency-bound otherwise
+  // (2 x 16 B in flight per thread at 37 % occupancy measured 2.9 TB/s; see profiles/r2_hot_kernels.md)
+  constexpr int U = MODE == 0 ? 4 : 2;
+  auto consume = [&](float4 g, const float4& v, const float4& o) {
+    if (MODE == 0) {
+      const float e0 = v.x - sh.x, e1 = v.y - sh.y, e2 = v.z - sh.z, e3 = v.w - sh.w;
+      a1.x += e0; a1.y += e1; a1.z += e2; a1.w += e3;
+      a2.x = fmaf(e0, e0, a2.x); a2.y = fmaf(e1, e1, a2.y); a2.z = fmaf(e2, e2, a2.z); a2.w = fmaf(e3, e3, a2.w);
+    } else if (MODE == 1) {
+      if (act == SEGSDE_ACT_RELU) {
+        float4 t = o;
+        if (!y.p) {
+          t.x = (v.x - mu.x) * sc.x + bt.x; t.y = (v.y - mu.y) * sc.y + bt.y;
+          t.z = (v.z - mu.z) * sc.z + bt.z; t.w = (v.w - mu.w) * sc.w + bt.w;
         }
-        a1.x += g.x; a1.y += g.y; a1.z += g.z; a1.w += g.w;
-        a2.x = fmaf(g.x, (v.x - mu.x) * is.x, a2.x); a2.y = fmaf(g.y, (v.y - mu.y) * is.y, a2.y);
-        a2.z = fmaf(g.z, (v.z - mu.z) * is.z, a2.z); a2.w = fmaf(g.w, (v.w - mu.w) * is.w, a2.w);
-      } else {
+        g.x = t.x > 0.f ? g.x : 0.f; g.y = t.y > 0.f ? g.y : 0.f; g.z = t.z > 0.f ? g.z : 0.f; g.w = t.w > 0.f ? g.w : 0.f;
+      }
+      a1.x += g.x; a1.y += g.y; a1.z += g.z; a1.w += g.w;
+      a2.x = fmaf(g.x, (v.x - mu.x) * is.x, a2.x); a2.y = fmaf(g.y, (v.y - mu.y) * is.y, a2.y);
+      a2.z = fmaf(g.z, (v.z - mu.z) * is.z, a2.z); a2.w = fmaf(g.w, (v.w - mu.w) * is.w, a2.w);
+    }
+    if (++cnt == 128) {       // bounded fp32 partials
+      d1[0] += a1.x; d1[1] += a1.y; d1[2] += a1.z; d1[3] += a1.w;
+      d2[0] += a2.x; d2[1] += a2.y; d2[2] += a2.z; d2[3] += a2.w;
+      a1 = make_float4(0.f, 0.f, 0.f, 0.f); a2 = a1; cnt = 0;
+    }
+  };
+  if (cv) {
+    const long long step = 8 * ppw;
+    long long p = pbeg + threadIdx.y * ppw + sub;
+    if (MODE != 2) {
+      const bool need_y = MODE == 1 && act == SEGSDE_ACT_RELU && y.p;
+      for (; p + (U - 1) * step < pend; p += U * step) {
+        float4 g[U], v[U], o[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const long long q = p + u * step;
+          v[u] = ld4(x.p + q * x.ld + c);
+          if (MODE == 1) g[u] = ld4(dy.p + q * dy.ld + c); else g[u] = v[u];
+          if (need_y) o[u] = ld4(y.p + q * y.ld + c); else o[u] = v[u];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) consume(g[u], v[u], o[u]);
+      }
+      for (; p < pend; p += step) {
+        const float4 v = ld4(x.p + p * x.ld + c);
+        const float4 g = MODE == 1 ? ld4(dy.p + p * dy.ld + c) : v;
+        const float4 o = need_y ? ld4(y.p + p * y.ld + c) : v;
+        consume(g, v, o);
+      }
+    } else {
+      for (; p < pend; p += step) {
         float4 g = ld4(dy.p + p * dy.ld + c);
         if (act != SEGSDE_ACT_NONE) {
           const float4 o = ld4(y.p + p * y.ld + c);
@@ -81,11 +110,10 @@ __global__ void __launch_bounds__(256) colreduce_fast_kernel(Rows x, Rows y, Row
         }
         if (dz.p) st4(dz.p + p * dz.ld + c, g);
         a1.x += g.x; a1.y += g.y; a1.z += g.z; a1.w += g.w;
-      }
-      if (++cnt == 128) {       // bounded fp32 partials
-        d1[0] += a1.x; d1[1] += a1.y; d1[2] += a1.z; d1[3] += a1.w;
-        d2[0] += a2.x; d2[1] += a2.y; d2[2] += a2.z; d2[3] += a2.w;
-        a1 = make_float4(0.f, 0.f, 0.f, 0.f); a2 = a1; cnt = 0;
+        if (++cnt == 128) {
+          d1[0] += a1.x; d1[1] += a1.y; d1[2] += a1.z; d1[3] += a1.w;
+          a1 = make_float4(0.f, 0.f, 0.f, 0.f); cnt = 0;
+        }
       }
     }
     d1[0] += a1.x; d1[1] += a1.y; d1[2] += a1.z; d1[3] += a1.w;
@@ -184,6 +212,9 @@ __global__ void __launch_bounds__(256) bn_apply_train_fast_kernel(Rows x, Rows r
   }
 }
 
+// dx = scale * (dz - mean(dz) - xhat * mean(dz * xhat)); the per-channel terms are turned into five fp32 coefficients
+// in shared memory once per CTA (the fp64 sums were converted per ELEMENT before: 8 LDG.64 + 8 F2F per float4 held the
+// pass at 2.8 TB/s).
 __global__ void __launch_bounds__(256) bn_bwd_apply_fast_kernel(Rows x, Rows y, Rows dy, Rows dx, Rows dres, long long total4,
                                                                 int cq, int cq_shift, int C,
                                                                 const float* __restrict__ mean,
@@ -191,38 +222,66 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_fast_kernel(Rows x, Rows y, 
                                                                 const float* __restrict__ gamma, int relu, int training,
                                                                 const double* __restrict__ red, float inv_count,
                                                                 const float* __restrict__ beta) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+  extern __shared__ __align__(16) float s_co[];      // [C] mean, invstd, scale, m0, m1, beta
+  float* s_mean = s_co; float* s_is = s_co + C; float* s_sc = s_co + 2 * C; float* s_m0 = s_co + 3 * C;
+  float* s_m1 = s_co + 4 * C; float* s_bt = s_co + 5 * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float is = invstd[c];
+    s_mean[c] = mean[c]; s_is[c] = is; s_sc[c] = is * (gamma ? gamma[c] : 1.f);
+    s_m0[c] = training ? (float)red[c] * inv_count : 0.f;
+    s_m1[c] = training ? (float)red[C + c] * inv_count : 0.f;
+    s_bt[c] = beta ? beta[c] : 0.f;
+  }
+  __syncthreads();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  auto one = [&](long long i, const float4& gin, const float4& xin, const float4& yin) {
     long long p; int c4;
     if (cq_shift >= 0) { p = i >> cq_shift; c4 = (int)(i & (cq - 1)); } else { p = i / cq; c4 = (int)(i - p * cq); }
     const int c = c4 * 4;
-    float g[4], xv[4], o[4];
-    { const float4 t = ld4(dy.p + p * dy.ld + c); g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w; }
-    { const float4 t = ld4(x.p + p * x.ld + c); xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w; }
+    const float4 m = ld4(s_mean + c), is4 = ld4(s_is + c), sc4 = ld4(s_sc + c);
+    float g[4] = {gin.x, gin.y, gin.z, gin.w};
+    const float xv[4] = {xin.x, xin.y, xin.z, xin.w};
     if (relu) {
-      float4 t;
-      if (y.p) t = ld4(y.p + p * y.ld + c);
-      else {       // recompute the forward value (no residual): same expression as bn_apply*_fast_kernel
-        const float4 m = ld4(mean + c), is4 = ld4(invstd + c);
-        const float4 g4 = gamma ? ld4(gamma + c) : make_float4(1.f, 1.f, 1.f, 1.f);
-        const float4 b4 = beta ? ld4(beta + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        t.x = (xv[0] - m.x) * (is4.x * g4.x) + b4.x; t.y = (xv[1] - m.y) * (is4.y * g4.y) + b4.y;
-        t.z = (xv[2] - m.z) * (is4.z * g4.z) + b4.z; t.w = (xv[3] - m.w) * (is4.w * g4.w) + b4.w;
+      float4 t = yin;
+      if (!y.p) {       // recompute the forward value (no residual): same expression as bn_apply*_fast_kernel
+        const float4 b4 = ld4(s_bt + c);
+        t.x = (xv[0] - m.x) * sc4.x + b4.x; t.y = (xv[1] - m.y) * sc4.y + b4.y;
+        t.z = (xv[2] - m.z) * sc4.z + b4.z; t.w = (xv[3] - m.w) * sc4.w + b4.w;
       }
       if (!(t.x > 0.f)) g[0] = 0.f; if (!(t.y > 0.f)) g[1] = 0.f; if (!(t.z > 0.f)) g[2] = 0.f; if (!(t.w > 0.f)) g[3] = 0.f;
     }
+    if (dx.p) {
+      const float4 m0 = ld4(s_m0 + c), m1 = ld4(s_m1 + c);
+      const float mm[4] = {m.x, m.y, m.z, m.w}, ii[4] = {is4.x, is4.y, is4.z, is4.w}, ss[4] = {sc4.x, sc4.y, sc4.z, sc4.w};
+      const float a0[4] = {m0.x, m0.y, m0.z, m0.w}, a1[4] = {m1.x, m1.y, m1.z, m1.w};
+      float o[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float is = invstd[c + k], sc = is * (gamma ? gamma[c + k] : 1.f);
-      if (training) {
-        const float xh = (xv[k] - mean[c + k]) * is;
-        const float m0 = (float)red[c + k] * inv_count, m1 = (float)red[C + c + k] * inv_count;
-        o[k] = sc * (g[k] - m0 - xh * m1);
-      } else {
-        o[k] = sc * g[k];
+      for (int k = 0; k < 4; ++k) {
+        const float xh = (xv[k] - mm[k]) * ii[k];
+        o[k] = training ? ss[k] * (g[k] - a0[k] - xh * a1[k]) : ss[k] * g[k];
       }
+      st4(dx.p + p * dx.ld + c, make_float4(o[0], o[1], o[2], o[3]));
     }
-    if (dx.p) st4(dx.p + p * dx.ld + c, make_float4(o[0], o[1], o[2], o[3]));
     if (dres.p) st4(dres.p + p * dres.ld + c, make_float4(g[0], g[1], g[2], g[3]));
+  };
+  auto addr = [&](const Rows& r, long long i) {
+    long long p; int c4;
+    if (cq_shift >= 0) { p = i >> cq_shift; c4 = (int)(i & (cq - 1)); } else { p = i / cq; c4 = (int)(i - p * cq); }
+    return r.p + p * r.ld + c4 * 4;
+  };
+  const bool need_y = relu && y.p;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + stride < total4; i += 2 * stride) {      // two float4 per tensor in flight
+    const float4 g0 = ld4(addr(dy, i)), g1 = ld4(addr(dy, i + stride));
+    const float4 x0 = ld4(addr(x, i)), x1 = ld4(addr(x, i + stride));
+    const float4 y0 = need_y ? ld4(addr(y, i)) : x0, y1 = need_y ? ld4(addr(y, i + stride)) : x1;
+    one(i, g0, x0, y0);
+    one(i + stride, g1, x1, y1);
+  }
+  if (i < total4) {
+    const float4 g0 = ld4(addr(dy, i)), x0 = ld4(addr(x, i));
+    const float4 y0 = need_y ? ld4(addr(y, i)) : x0;
+    one(i, g0, x0, y0);
   }
 }
 
@@ -232,7 +291,8 @@ static void reduce_geometry(long long P, int C, dim3& grid, long long& slab) {
   const int cq = C / 4;
   const int cblocks = cdiv(cq, 32);
   const int cq_w = cq < 32 ? cq : 32, ppw = 32 / cq_w;
-  long long want = (148LL * 8) / cblocks; if (want < 1) want = 1;
+  // 148 * 12 CTAs = whole waves at 3, 4 or 6 resident CTAs per SM (80 / 64 / 44 registers for MODE 1 / 0 / 2)
+  long long want = (148LL * 12) / cblocks; if (want < 1) want = 1;
   long long s = cdiv(P, 8LL * ppw * 16); if (s > want) s = want; if (s < 1) s = 1;
   slab = (P + s - 1) / s;
   grid = dim3((unsigned)cdiv(P, slab), cblocks);
@@ -303,7 +363,7 @@ int bn_bwd_apply_fast(const View& x, const View& y, const View& dy, const View& 
   const long long total4 = P * cq;
   long long blocks = cdiv(total4, 256 * 4); if (blocks > 148 * 16) blocks = 148 * 16; if (blocks < 1) blocks = 1;
   Rows none; none.p = nullptr; none.ld = 0;
-  bn_bwd_apply_fast_kernel<<<(unsigned)blocks, 256, 0, st>>>(rows_of(x), y.p ? rows_of(y) : none, rows_of(dy),
+  bn_bwd_apply_fast_kernel<<<(unsigned)blocks, 256, 6 * x.c * sizeof(float), st>>>(rows_of(x), y.p ? rows_of(y) : none, rows_of(dy),
                                                             dx.p ? rows_of(dx) : none, dres.p ? rows_of(dres) : none, total4, cq,
                                                             shift_of(cq), x.c, mean, invstd, gamma, relu, training, red,
                                                             (float)(1.0 / (double)count), beta);

@@ -6,28 +6,25 @@
 namespace segsde {
 
 // y[n, hp, wp, c] = x[n, refl(hp - pad) >> up, refl(wp - pad) >> up, c]
-__global__ void pad_prep_kernel(View x, View y, int up, int pad, int Hc, int Wc) {
-  const int cq = y.c / 4;
-  const long long total = (long long)y.n * y.h * y.w * cq;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int c = (int)(idx % cq) * 4; long long q = idx / cq;
-  const int wp = (int)(q % y.w); q /= y.w;
-  const int hp = (int)(q % y.h); const int n = (int)(q / y.h);
+// grid (chunks of one padded row, hp, n): 32-bit index math only - the 64-bit div/mod chain of a flat index made this
+// copy issue-bound at 3.3 TB/s (profiles/r2_hot_kernels.md).
+__global__ void __launch_bounds__(256) pad_prep_kernel(View x, View y, int up, int pad, int Hc, int Wc, int cq) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= y.w * cq) return;
+  const int wp = i / cq, c = (i - wp * cq) * 4;
+  const int hp = blockIdx.y, n = blockIdx.z;
   const int h = reflect_idx(hp - pad, Hc) >> up, w = reflect_idx(wp - pad, Wc) >> up;
   *reinterpret_cast<float4*>(y.p + y.off(n, hp, wp) + c) =
       *reinterpret_cast<const float4*>(x.p + x.off(n, h, w) + c);
 }
 
 // adjoint of pad_prep: dx[n,h,w,c] = sum over the (1<<up)^2 fine positions of the sum over their reflect preimages
-__global__ void pad_fold_kernel(View dyp, View dx, int up, int pad, int Hc, int Wc) {
-  const int cq = dx.c / 4;
-  const long long total = (long long)dx.n * dx.h * dx.w * cq;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int c = (int)(idx % cq) * 4; long long q = idx / cq;
-  const int w = (int)(q % dx.w); q /= dx.w;
-  const int h = (int)(q % dx.h); const int n = (int)(q / dx.h);
+// grid (chunks of one dx row, h, n)
+__global__ void __launch_bounds__(256) pad_fold_kernel(View dyp, View dx, int up, int pad, int Hc, int Wc, int cq) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= dx.w * cq) return;
+  const int w = i / cq, c = (i - w * cq) * 4;
+  const int h = blockIdx.y, n = blockIdx.z;
   const int f = 1 << up;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int a = 0; a < f; ++a) {
@@ -42,9 +39,9 @@ __global__ void pad_fold_kernel(View dyp, View dx, int up, int pad, int Hc, int 
       cols[nc++] = ww;
       if (ww >= 1 && ww <= pad) cols[nc++] = -ww;
       if (ww >= Wc - 1 - pad && ww <= Wc - 2) cols[nc++] = 2 * (Wc - 1) - ww;
-      for (int i = 0; i < nr; ++i)
+      for (int ii = 0; ii < nr; ++ii)
         for (int j = 0; j < nc; ++j) {
-          const float4 v = *reinterpret_cast<const float4*>(dyp.p + dyp.off(n, rows[i] + pad, cols[j] + pad) + c);
+          const float4 v = *reinterpret_cast<const float4*>(dyp.p + dyp.off(n, rows[ii] + pad, cols[j] + pad) + c);
           acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
     }
@@ -125,14 +122,11 @@ __global__ void weight_phase_s2_kernel(const float* __restrict__ w, float* __res
 // upsampled + padded copy (4x the low-res bytes) is never written, its gradient never folded back.
 //
 // xp[n, u, v, c] = x[n, clamp(u - 1), clamp(v - 1), c]   (replicate padding by 1)
-__global__ void pad_replicate_kernel(View x, View y) {
-  const int cq = y.c / 4;
-  const long long total = (long long)y.n * y.h * y.w * cq;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int c = (int)(idx % cq) * 4; long long q = idx / cq;
-  const int v = (int)(q % y.w); q /= y.w;
-  const int u = (int)(q % y.h); const int n = (int)(q / y.h);
+__global__ void __launch_bounds__(256) pad_replicate_kernel(View x, View y, int cq) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= y.w * cq) return;
+  const int v = i / cq, c = (i - v * cq) * 4;
+  const int u = blockIdx.y, n = blockIdx.z;
   const int h = min(max(u - 1, 0), x.h - 1), w = min(max(v - 1, 0), x.w - 1);
   *reinterpret_cast<float4*>(y.p + y.off(n, u, v) + c) = *reinterpret_cast<const float4*>(x.p + x.off(n, h, w) + c);
 }
@@ -248,8 +242,9 @@ extern "C" int segsde_pad_prep(const segsde_nhwc_t* x, const segsde_nhwc_t* y, i
   const int Hc = vx.h << up, Wc = vx.w << up;
   if (vy.h != Hc + 2 * pad || vy.w != Wc + 2 * pad || vy.c != vx.c || vy.n != vx.n || pad >= Hc || pad >= Wc) return SEGSDE_E_ARG;
   if (!vec4_ok(vx) || !vec4_ok(vy)) return SEGSDE_E_ALIGN;
-  const long long total = (long long)vy.n * vy.h * vy.w * (vy.c / 4);
-  pad_prep_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(vx, vy, up, pad, Hc, Wc);
+  if (vy.h > 65535 || vy.n > 65535) return SEGSDE_E_ARG;
+  const int cq = vy.c / 4;
+  pad_prep_kernel<<<dim3(cdiv(vy.w * cq, 256), vy.h, vy.n), 256, 0, as_stream(stream)>>>(vx, vy, up, pad, Hc, Wc, cq);
   return launched();
 }
 extern "C" int segsde_pad_fold(const segsde_nhwc_t* dyp, const segsde_nhwc_t* dx, int up, int pad, void* stream) {
@@ -258,8 +253,9 @@ extern "C" int segsde_pad_fold(const segsde_nhwc_t* dyp, const segsde_nhwc_t* dx
   const int Hc = vx.h << up, Wc = vx.w << up;
   if (vd.h != Hc + 2 * pad || vd.w != Wc + 2 * pad || vd.c != vx.c || vd.n != vx.n) return SEGSDE_E_ARG;
   if (!vec4_ok(vx) || !vec4_ok(vd)) return SEGSDE_E_ALIGN;
-  const long long total = (long long)vx.n * vx.h * vx.w * (vx.c / 4);
-  pad_fold_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(vd, vx, up, pad, Hc, Wc);
+  if (vx.h > 65535 || vx.n > 65535) return SEGSDE_E_ARG;
+  const int cq = vx.c / 4;
+  pad_fold_kernel<<<dim3(cdiv(vx.w * cq, 256), vx.h, vx.n), 256, 0, as_stream(stream)>>>(vd, vx, up, pad, Hc, Wc, cq);
   return launched();
 }
 extern "C" int segsde_weight_transpose_flip(const float* w, float* wt, int cout, int kh, int kw, int ctot,
@@ -274,8 +270,9 @@ extern "C" int segsde_pad_replicate(const segsde_nhwc_t* x, const segsde_nhwc_t*
   View vx = mk(x), vy = mk(y);
   if (vy.h != vx.h + 2 || vy.w != vx.w + 2 || vy.c != vx.c || vy.n != vx.n) return SEGSDE_E_ARG;
   if (!vec4_ok(vx) || !vec4_ok(vy)) return SEGSDE_E_ALIGN;
-  const long long total = (long long)vy.n * vy.h * vy.w * (vy.c / 4);
-  pad_replicate_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(vx, vy);
+  if (vy.h > 65535 || vy.n > 65535) return SEGSDE_E_ARG;
+  const int cq = vy.c / 4;
+  pad_replicate_kernel<<<dim3(cdiv(vy.w * cq, 256), vy.h, vy.n), 256, 0, as_stream(stream)>>>(vx, vy, cq);
   return launched();
 }
 extern "C" int segsde_weight_phase_up(const float* w, float* wp, int cout, int ctot, int c_begin, int c_count, int a, int b,

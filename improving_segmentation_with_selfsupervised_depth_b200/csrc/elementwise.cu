@@ -7,16 +7,17 @@
 namespace segsde {
 
 // decompose a flat (pixel, channel-vector) index of view V
+// grid = (chunks of one image, n): 32-bit index math only (a flat 64-bit index costs three 64-bit div/mod chains per
+// element vector, which made the copy-class kernels issue-bound; profiles/r2_hot_kernels.md)
 #define EW_DECOMP(V, VEC)                                                     \
-  const int cq_ = (V).c / (VEC);                                              \
-  const long long total_ = (long long)(V).n * (V).h * (V).w * cq_;            \
-  const long long idx_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;    \
-  if (idx_ >= total_) return;                                                 \
-  const int c_ = (int)(idx_ % cq_) * (VEC);                                   \
-  long long q_ = idx_ / cq_;                                                  \
-  const int w_ = (int)(q_ % (V).w); q_ /= (V).w;                              \
-  const int h_ = (int)(q_ % (V).h);                                           \
-  const int n_ = (int)(q_ / (V).h);
+  const unsigned cq_ = (unsigned)((V).c / (VEC));                             \
+  const unsigned idx_ = blockIdx.x * 256u + threadIdx.x;                      \
+  if (idx_ >= (unsigned)(V).h * (unsigned)(V).w * cq_) return;                \
+  const unsigned q_ = idx_ / cq_;                                             \
+  const int c_ = (int)(idx_ - q_ * cq_) * (VEC);                              \
+  const int h_ = (int)(q_ / (unsigned)(V).w);                                 \
+  const int w_ = (int)(q_ - (unsigned)h_ * (unsigned)(V).w);                  \
+  const int n_ = (int)blockIdx.y;
 
 template <int VEC> struct Vec;
 template <> struct Vec<1> {
@@ -34,8 +35,8 @@ template <> struct Vec<4> {
   }
 };
 
-static inline int ew_blocks(const View& v, int vec) {
-  return cdiv((long long)v.n * v.h * v.w * (v.c / vec), 256);
+static inline dim3 ew_blocks(const View& v, int vec) {
+  return dim3((unsigned)cdiv((long long)v.h * v.w * (v.c / vec), 256), (unsigned)v.n);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -197,8 +198,13 @@ __global__ void maxpool_fwd_kernel(View x, View y, uint8_t* __restrict__ idx) {
   for (int i = 0; i < VEC; ++i) o.v[i] = best[i];
   o.store(y.p + y.off(n_, h_, w_) + c_);
   uint8_t* ip = idx + (((long long)n_ * y.h + h_) * y.w + w_) * y.c + c_;
+  if (VEC == 4) {
+    *reinterpret_cast<uchar4*>(ip) = make_uchar4((uint8_t)bi[0], (uint8_t)bi[VEC > 1 ? 1 : 0], (uint8_t)bi[VEC > 2 ? 2 : 0],
+                                                 (uint8_t)bi[VEC > 3 ? 3 : 0]);
+  } else {
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) ip[i] = (uint8_t)bi[i];
+    for (int i = 0; i < VEC; ++i) ip[i] = (uint8_t)bi[i];
+  }
 }
 
 // gather form: every input element collects from the <=4 windows that contain it (no atomics)
@@ -215,9 +221,17 @@ __global__ void maxpool_bwd_kernel(View dy, const uint8_t* __restrict__ idx, Vie
       const int tap = (h_ - (2 * oh - 1)) * 3 + (w_ - (2 * ow - 1));
       const uint8_t* ip = idx + (((long long)n_ * dy.h + oh) * dy.w + ow) * dy.c + c_;
       Vec<VEC> g; g.load(dy.p + dy.off(n_, oh, ow) + c_);
+      if (VEC == 4) {
+        const uchar4 iv = *reinterpret_cast<const uchar4*>(ip);
+        const int t4[4] = {iv.x, iv.y, iv.z, iv.w};
 #pragma unroll
-      for (int i = 0; i < VEC; ++i)
-        if (ip[i] == tap) acc[i] += g.v[i];
+        for (int i = 0; i < VEC; ++i)
+          if (t4[i] == tap) acc[i] += g.v[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i)
+          if (ip[i] == tap) acc[i] += g.v[i];
+      }
     }
   Vec<VEC> o;
 #pragma unroll
@@ -483,7 +497,7 @@ extern "C" int segsde_bn_bwd_apply(const segsde_nhwc_t* x, const segsde_nhwc_t* 
   View vx = mk(x), vy = mk(y), vd = mk(dy), vdx = mk(dx), vdr = mk(dres);
   if (relu && !vy.p && vdr.p) return SEGSDE_E_ARG;      // with a residual the mask needs the saved output
   int rc = SEGSDE_OK;
-  const bool fast = pix_contig(vx) && pix_contig(vd) && (!relu || !vy.p || pix_contig(vy)) && (!vdx.p || pix_contig(vdx)) &&
+  const bool fast = vx.c <= 2048 && pix_contig(vx) && pix_contig(vd) && (!relu || !vy.p || pix_contig(vy)) && (!vdx.p || pix_contig(vdx)) &&
                     (!vdr.p || pix_contig(vdr));
   if ((vdx.p || vdr.p) && fast) {
     rc = bn_bwd_apply_fast(vx, vy, vd, vdx, vdr, mean, invstd, gamma, relu, training, red, count, as_stream(stream), beta);

@@ -29,6 +29,9 @@ torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); step(); e1.record(); torch.cuda.synchronize()
 print('unprofiled step ms', e0.elapsed_time(e1))
+import time
+torch.cuda.synchronize(); t0 = time.perf_counter(); step(); t1 = time.perf_counter(); torch.cuda.synchronize()
+print('host issue time of one step (queue empty, no sync inside): %.1f ms' % ((t1 - t0) * 1e3))
 A.PROFILE = []; ops.PROFILE = []; ops.PROFILE_DESC = []; ops.ROUTES = []
 e0.record(); step(); e1.record(); torch.cuda.synchronize()
 print('profiled step ms', e0.elapsed_time(e1))
