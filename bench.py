@@ -400,6 +400,7 @@ def run_b200(args):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         last = None
+        marks = []           # one event per step: the per-step spread is reported beside the K-step total
         if e2e:
             # every step's inputs travel pinned host -> device inside the timed region; the copy of step i+1 is
             # issued on a side stream into the other of two preallocated device buffer sets while step i computes
@@ -426,6 +427,8 @@ def run_b200(args):
                     upload(slot ^ 1, i == 0)
                 loss_t = step(dev_bufs[slot])
                 consumed[slot].record(main)
+                marks.append(torch.cuda.Event(enable_timing=True))
+                marks[-1].record()
                 # D2H read of the step's loss, every step: an async copy into pinned memory, consumed one step late
                 # (the way a training loop logs) so that the host keeps issuing step i+1 while step i runs
                 loss_host[i % 2].copy_(loss_t.detach().reshape(1), non_blocking=True)
@@ -438,9 +441,14 @@ def run_b200(args):
         else:
             for _ in range(nsteps):
                 last = step(resident)
+                marks.append(torch.cuda.Event(enable_timing=True))
+                marks[-1].record()
         ev1.record()
         barrier()
         ms = ev0.elapsed_time(ev1)
+        marks = [ev0] + marks
+        step_ms = sorted(a.elapsed_time(b) for a, b in zip(marks[:-1], marks[1:]))
+        timed.spread = {"median": step_ms[len(step_ms) // 2], "max": step_ms[-1]} if step_ms else None
         t = torch.tensor([ms], device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -457,8 +465,10 @@ def run_b200(args):
     # pass 1 (the reported number): nothing instrumented
     n0 = A.launch_count()
     ms, last = timed(args.steps, e2e=False)
+    spread = timed.spread
     launches = A.launch_count() - n0
     ms_e2e, last_e2e = timed(args.steps, e2e=True)
+    spread_e2e = timed.spread
     clk = clocks.stop() if rank == 0 else None
     # pass 2 (roofline only): every convolution launch and the fused reprojection launch bracketed by CUDA events on
     # the launching stream — the event pairs cost ~1 % of the step, so they stay out of the reported number
@@ -554,7 +564,8 @@ def run_b200(args):
                    "l2": "inputs+activations per step >> 126 MB L2 (no flush needed)",
                    "train_gflop_per_image": gf},
         "e2e": {"value": gb * args.steps / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d_bytes,
-                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "ms_per_step_spread": spread_e2e},
+        "ms_per_step_spread": spread,
         "gpu_launches": launches, "clocks": clk, "roofline": roof, "roofline_hbm_kernel": roof_hbm, "cpu_baseline": cpu,
         "loss": float(last.detach()) if hasattr(last, "detach") else float(last),
         "conv_roofline_frac_whole_step": gf * 1e9 * gb * args.steps / (ms * 1e-3) / 1e12 / peak_tf / world,

@@ -189,9 +189,15 @@ class _Conv2dFn(torch.autograd.Function):
                     results.append(None)
                     continue
                 if tc_dgrad and cn % 64 == 0:
-                    wt = torch.empty(cn * kh * kw * cout, device=dev, dtype=torch.float32)
-                    A.call("segsde_weight_transpose_flip", A.ptr(w), A.ptr(wt), C.c_int(cout), C.c_int(kh), C.c_int(kw),
-                           C.c_int(ctot), C.c_int(c0), C.c_int(cn), st)
+                    # the transposed / tap-flipped weights are kept on the graph node: the second backward over a
+                    # retained graph (train.py:486 then :510) reuses them; they die with the graph
+                    cache = ctx.__dict__.setdefault("_wt_cache", {})
+                    wt = cache.get((c0, cn))
+                    if wt is None:
+                        wt = torch.empty(cn * kh * kw * cout, device=dev, dtype=torch.float32)
+                        A.call("segsde_weight_transpose_flip", A.ptr(w), A.ptr(wt), C.c_int(cout), C.c_int(kh),
+                               C.c_int(kw), C.c_int(ctot), C.c_int(c0), C.c_int(cn), st)
+                        cache[(c0, cn)] = wt
                     if sub2 and idx == 0:      # gradient of the ::2 view: written through the view, zeros elsewhere
                         full1 = ops.cl_empty(*full_shape1, dev, zero=True)
                         gx = full1[:, :, ::2, ::2]

@@ -50,15 +50,27 @@ __global__ void __launch_bounds__(256) pad_fold_kernel(View dyp, View dx, int up
 }
 
 // wt[ci - c0][kh-1-r][kw-1-s][co] = w[co][r][s][ci]
-__global__ void weight_tflip_kernel(const float* __restrict__ w, float* __restrict__ wt, int Cout, int kh, int kw,
-                                    int Ctot, int c0, int cn) {
-  const long long total = (long long)cn * kh * kw * Cout;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int co = (int)(idx % Cout); long long q = idx / Cout;
-  const int s = (int)(q % kw); q /= kw;
-  const int r = (int)(q % kh); const int ci = (int)(q / kh);
-  wt[idx] = w[(((long long)co * kh + (kh - 1 - r)) * kw + (kw - 1 - s)) * Ctot + c0 + ci];
+// Per tap a [Cout x cn] -> [cn x Cout] transpose through a 32 x 33 shared-memory tile: reads coalesced along ci, writes
+// coalesced along co (the flat one-thread-per-element form gathered with a kh*kw*Ctot stride: ~5 ms/step of the
+// DepthMix configuration, whose encoder trains).  grid (ci tiles, co tiles, taps), block (32, 8)
+__global__ void __launch_bounds__(256) weight_tflip_kernel(const float* __restrict__ w, float* __restrict__ wt, int Cout, int kh,
+                                                           int kw, int Ctot, int c0, int cn) {
+  __shared__ float tile[32][33];
+  const int taps = kh * kw, tap = blockIdx.z;
+  const int r = tap / kw, s_ = tap - r * kw;
+  const int tap_o = (kh - 1 - r) * kw + (kw - 1 - s_);
+  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int co = co0 + threadIdx.y + 8 * j, ci = ci0 + threadIdx.x;
+    if (co < Cout && ci < cn) tile[threadIdx.y + 8 * j][threadIdx.x] = w[((long long)co * taps + tap) * Ctot + c0 + ci];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int ci = ci0 + threadIdx.y + 8 * j, co = co0 + threadIdx.x;
+    if (co < Cout && ci < cn) wt[((long long)ci * taps + tap_o) * Cout + co] = tile[threadIdx.x][threadIdx.y + 8 * j];
+  }
 }
 
 // The same pass for FEW channels (the 1-channel disparity heads, the 12-channel pose output): one thread per pixel, the
@@ -261,8 +273,9 @@ extern "C" int segsde_pad_fold(const segsde_nhwc_t* dyp, const segsde_nhwc_t* dx
 extern "C" int segsde_weight_transpose_flip(const float* w, float* wt, int cout, int kh, int kw, int ctot,
                                             int c_begin, int c_count, void* stream) {
   if (!w || !wt || cout < 1 || kh < 1 || kw < 1 || c_begin < 0 || c_count < 1 || c_begin + c_count > ctot) return SEGSDE_E_ARG;
-  const long long total = (long long)c_count * kh * kw * cout;
-  weight_tflip_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(w, wt, cout, kh, kw, ctot, c_begin, c_count);
+  if (kh * kw > 65535 || cdiv(cout, 32) > 65535) return SEGSDE_E_ARG;
+  weight_tflip_kernel<<<dim3(cdiv(c_count, 32), cdiv(cout, 32), kh * kw), dim3(32, 8), 0, as_stream(stream)>>>(
+      w, wt, cout, kh, kw, ctot, c_begin, c_count);
   return launched();
 }
 extern "C" int segsde_pad_replicate(const segsde_nhwc_t* x, const segsde_nhwc_t* y, void* stream) {

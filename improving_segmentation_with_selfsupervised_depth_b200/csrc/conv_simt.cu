@@ -320,6 +320,12 @@ __global__ void __launch_bounds__(256) conv1x1_fewpx_kernel(View x, View y, cons
   if (lane == 0) y.p[y.off(n, hq, wq) + co] = act_apply(s + (bias ? bias[co] : 0.f), act);
 }
 
+// conv_fewcout.cu
+bool fewcout_ok(const View& x, const View& y, int kh, int kw, int stride, int pad, bool second_source, bool nchw, bool up1);
+int fewcout_fwd(const View& x, const View& y, const float* w, const float* bias, int act, cudaStream_t st);
+int fewcout_dgrad(const View& dy, const View& dx, const float* w, cudaStream_t st);
+int fewcout_wgrad(const View& x, const View& dy, float* dw, cudaStream_t st);
+
 static int fill(ConvP& p, const segsde_nhwc_t* x1, const segsde_nhwc_t* x2, const segsde_nhwc_t* y,
                 const segsde_conv_desc_t* d, bool x_optional) {
   if (!y || !y->ptr || !d) return SEGSDE_E_ARG;
@@ -363,6 +369,10 @@ extern "C" int segsde_conv2d_fwd(const segsde_nhwc_t* x1, const segsde_nhwc_t* x
                                                                                        p.act, p.P);
     return launched();
   }
+  if (fewcout_ok(p.x1, p.y, p.kh, p.kw, p.stride, p.pad, p.x2.p != nullptr, p.nchw != 0, p.up1 != 0)) {
+    rc = fewcout_fwd(p.x1, p.y, w, bias, p.act, as_stream(stream));
+    if (rc != SEGSDE_E_UNSUPPORTED) return rc;
+  }
   p.w = w; p.bias = bias;
   dim3 grid(cdiv(p.P, BM), cdiv(p.Cout, BN));
   conv_fwd_kernel<<<grid, CT, 0, as_stream(stream)>>>(p);
@@ -382,6 +392,9 @@ extern "C" int segsde_conv2d_dgrad(const segsde_nhwc_t* dy, const float* w, cons
     rc = c1_dgrad(p.y, w, p.x1, d, as_stream(stream));
     if (rc != SEGSDE_E_UNSUPPORTED) return rc;
   }
+  if (p.x1.p && (!dx2 || !dx2->ptr) && p.C2 == 0 &&
+      fewcout_ok(p.x1, p.y, p.kh, p.kw, p.stride, p.pad, false, p.nchw != 0, p.up1 != 0))
+    return fewcout_dgrad(p.y, p.x1, w, as_stream(stream));
   p.w = w; p.bias = nullptr;
   const bool refl = p.pad_mode == SEGSDE_PAD_REFLECT;
   const int off = refl ? p.pad : 0;
@@ -404,6 +417,8 @@ extern "C" int segsde_conv2d_wgrad(const segsde_nhwc_t* x1, const segsde_nhwc_t*
     rc = c1_wgrad(p.x1, p.y, dw, d, as_stream(stream));
     if (rc != SEGSDE_E_UNSUPPORTED) return rc;
   }
+  if (!dbias && fewcout_ok(p.x1, p.y, p.kh, p.kw, p.stride, p.pad, p.x2.p != nullptr, p.nchw != 0, p.up1 != 0))
+    return fewcout_wgrad(p.x1, p.y, dw, as_stream(stream));
   p.w = nullptr; p.bias = nullptr;
   const int gx = cdiv(p.Cout, BM), gy = cdiv(p.Ktot, BN);
   long long want = (148LL * 6) / ((long long)gx * gy);

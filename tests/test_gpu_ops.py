@@ -49,6 +49,13 @@ CASES = [
     (200, 0, 24, 1, 1, 0, 1, False, False, 0, False, 2, 3),
     # pose head shape class (pose_decoder.py:33): few output channels, many pixels -> finely split wgrad
     (64, 0, 12, 1, 1, 0, 1, False, False, 0, True, 16, 32),
+    # segmentation-head shape class (joint_segmentation_depth_decoder.py:106-107): 1x1, Cout = 19 classes on >= 4096
+    # pixels -> the few-output-channel kernels of conv_fewcout.cu (fprop / dgrad / wgrad); partial channel chunks too
+    (64, 0, 19, 1, 1, 0, 1, False, False, 0, True, 48, 64),
+    (128, 0, 19, 1, 1, 0, 1, False, False, 0, False, 40, 60),
+    (36, 0, 5, 1, 1, 0, 1, False, False, 2, True, 50, 50),
+    (256, 0, 12, 1, 1, 0, 1, False, False, 0, True, 48, 48),
+    (96, 0, 32, 1, 1, 0, 1, False, False, 1, False, 47, 53),
 ]
 
 
