@@ -29,6 +29,9 @@ PHASE_DGRAD_S2 = os.environ.get("SEGSDE_PHASE_DGRAD", "1") != "0"
 
 # nearest x2 upsample + reflect pad + 3x3 conv (no skip) as four 2x2 phase convolutions on the low-res input
 # (SEGSDE_PHASE_UPCONV=0 restores the materialised form)
+# disparity heads: 32-plane tcgen05 GEMMs (default; measured 1.99 ms fwd+bwd at 12x512x1024) or 12-plane fp32 CUDA-core
+# GEMMs of conv_fewcout.cu (SEGSDE_HEAD_FEWCOUT=1; 3.06 ms - latency-bound, kept as the fp32 cross-check of the heads)
+HEAD_FEWCOUT = os.environ.get("SEGSDE_HEAD_FEWCOUT", "0") == "1"
 PHASE_UPCONV = os.environ.get("SEGSDE_PHASE_UPCONV", "1") != "0"
 
 
@@ -464,9 +467,11 @@ class _StemConvFn(torch.autograd.Function):
 
 
 class _HeadConvFn(torch.autograd.Function):
-    """C -> 1, 3x3, pad 1 (the sigmoid disparity heads, depth_decoder.py:69-70,107-112) on the tensor cores:
-    z = 1x1conv(x) to 9 tap planes (N padded to 32) + a 9-tap stencil; backward = adjoint stencil of dy (gcol) +
-    two 1x1 GEMMs (dgrad: gcol x Wz, wgrad: x^T x gcol)."""
+    """C -> 1, 3x3, pad 1 (the sigmoid disparity heads, depth_decoder.py:69-70,107-112):
+    z = 1x1conv(x) to 9 tap planes + a 9-tap stencil; backward = adjoint stencil of dy (gcol) + two 1x1 GEMMs
+    (dgrad: gcol x Wz, wgrad: x^T x gcol).  Default: N padded to 32 planes on the tcgen05 kernels;
+    SEGSDE_HEAD_FEWCOUT=1: 12 planes (9 used) on the few-output-channel fp32 kernels of conv_fewcout.cu (measured
+    slower, kept as the fp32 form of the same decomposition)."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, pad_mode, act):
@@ -479,22 +484,32 @@ class _HeadConvFn(torch.autograd.Function):
         reflect = int(pad_mode == A.PAD_REFLECT)
         b = bias.detach() if bias is not None else None
         flops = 2.0 * n * h * wd * 9 * c
-        wz = ops.zeros_f32(32 * c, dev)
+        few = HEAD_FEWCOUT
+        planes = 12 if few else 32
+        wz = ops.zeros_f32(planes * c, dev)
         A.call("segsde_copy_rows", A.ptr(w), C.c_int(c), A.ptr(wz), C.c_int(c), C.c_int(9), C.c_int(c), st)
-        z = ops.cl_empty(n, 32, h, wd, dev)
+        z = ops.cl_empty(n, planes, h, wd, dev)
         d1 = ops._desc(1, 1, 1, 0, 1, A.PAD_ZERO, False, A.ACT_NONE, False)
-        desc = "head %d->1 k3 out %dx%d (1x1 GEMM + stencil)" % (c, h, wd)
-        _fwd(x, None, wz, None, z, d1, "fprop", flops, desc)
+        desc = "head %d->1 k3 out %dx%d (1x1 GEMM%s + stencil)" % (c, h, wd, " fp32" if few else "")
+        if few:
+            vx, vz = ops.view(x), ops.view(z)
+
+            def launch():
+                A.call("segsde_conv2d_fwd", C.byref(vx), None, A.ptr(wz), None, C.byref(vz), C.byref(d1), st)
+                ops.log_route("fprop", False, "cc:fewcout")
+            ops._timed("fprop", flops, launch, desc)
+        else:
+            _fwd(x, None, wz, None, z, d1, "fprop", flops, desc)
         A.call("segsde_head_stencil_fwd", C.byref(ops.view(z)), C.byref(ops.view(y)), A.ptr(b), C.c_int(act),
                C.c_int(reflect), C.c_int(1), st)
         ctx.save_for_backward(x, w, wz, y if act != A.ACT_NONE else None)
-        ctx.cfg = (reflect, act, bias is not None, desc)
+        ctx.cfg = (reflect, act, bias is not None, desc, few, planes)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, w, wz, y = ctx.saved_tensors
-        reflect, act, has_bias, desc = ctx.cfg
+        reflect, act, has_bias, desc, few, planes = ctx.cfg
         n, c, h, wd = x.shape
         dev, st = x.device, A.stream_ptr()
         dy = ops.as_cl(dy)
@@ -509,26 +524,35 @@ class _HeadConvFn(torch.autograd.Function):
             dz = dy
         dx = dw = None
         if need_x or need_w:
-            gcol = ops.cl_empty(n, 32, h, wd, dev)
+            gcol = ops.cl_empty(n, planes, h, wd, dev)
             A.call("segsde_head_gcol", C.byref(ops.view(dz)), C.byref(ops.view(gcol)), C.c_int(reflect), C.c_int(1), st)
             d1 = ops._desc(1, 1, 1, 0, 1, A.PAD_ZERO, False, A.ACT_NONE, False)
+            fl = 2.0 * n * h * wd * 9 * c
             if need_x:
-                wzt = torch.empty(c * 32, device=dev, dtype=torch.float32)
-                A.call("segsde_weight_transpose_flip", A.ptr(wz), A.ptr(wzt), C.c_int(32), C.c_int(1), C.c_int(1),
-                       C.c_int(c), C.c_int(0), C.c_int(c), st)
                 dx = ops.cl_empty(n, c, h, wd, dev)
-                _fwd(gcol, None, wzt, None, dx, d1, "dgrad", 2.0 * n * h * wd * 9 * c, desc)
+                if few:
+                    vg, vdx = ops.view(gcol), ops.view(dx)
+
+                    def launch_x():
+                        A.call("segsde_conv2d_dgrad", C.byref(vg), A.ptr(wz), C.byref(vdx), None, C.byref(d1), st)
+                        ops.log_route("dgrad", False, "cc:fewcout")
+                    ops._timed("dgrad", fl, launch_x, desc)
+                else:
+                    wzt = torch.empty(c * planes, device=dev, dtype=torch.float32)
+                    A.call("segsde_weight_transpose_flip", A.ptr(wz), A.ptr(wzt), C.c_int(planes), C.c_int(1), C.c_int(1),
+                           C.c_int(c), C.c_int(0), C.c_int(c), st)
+                    _fwd(gcol, None, wzt, None, dx, d1, "dgrad", fl, desc)
             if need_w:
-                dwz = ops.zeros_f32(32 * c, dev)
+                dwz = ops.zeros_f32(planes * c, dev)
                 v1, vg = ops.view(x), ops.view(gcol)
 
                 def launch_w():
-                    if A.try_call("segsde_conv2d_wgrad_tc", C.byref(v1), None, C.byref(vg), A.ptr(dwz), None,
-                                  C.byref(d1), st):
+                    if not few and A.try_call("segsde_conv2d_wgrad_tc", C.byref(v1), None, C.byref(vg), A.ptr(dwz), None,
+                                              C.byref(d1), st):
                         return ops.log_route("wgrad", True)
                     A.call("segsde_conv2d_wgrad", C.byref(v1), None, C.byref(vg), A.ptr(dwz), None, C.byref(d1), st)
-                    ops.log_route("wgrad", False)
-                ops._timed("wgrad", 2.0 * n * h * wd * 9 * c, launch_w, desc)
+                    ops.log_route("wgrad", False, "cc:fewcout" if few else None)
+                ops._timed("wgrad", fl, launch_w, desc)
                 dw = torch.empty_like(w)
                 A.call("segsde_copy_rows", A.ptr(dwz), C.c_int(c), A.ptr(dw), C.c_int(c), C.c_int(9), C.c_int(c), st)
         return dx, dw, db, None, None

@@ -330,10 +330,11 @@ extern "C" int segsde_act_bwd_bias(const segsde_nhwc_t* y, const segsde_nhwc_t* 
   if (fast_reduce_ok(vd) && (act == SEGSDE_ACT_NONE || pix_contig(vy)) && (!vz.p || pix_contig(vz)))
     return act_bwd_bias_fast(vy, vd, vz, act, dbias, as_stream(stream));
   const long long P = (long long)vd.n * vd.h * vd.w;
-  if (vd.c <= 16) {
+  if (vd.c <= 16 || (vd.c <= 32 && vd.c % 4 != 0)) {      // incl. the 19-class segmentation heads' bias gradient
     long long blocks = cdiv(P, 256 * 4); if (blocks > 148 * 8) blocks = 148 * 8; if (blocks < 1) blocks = 1;
     if (vd.c <= 4) act_bwd_bias_fewc_kernel<4><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(vy, vd, vz, act, dbias);
-    else act_bwd_bias_fewc_kernel<16><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(vy, vd, vz, act, dbias);
+    else if (vd.c <= 16) act_bwd_bias_fewc_kernel<16><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(vy, vd, vz, act, dbias);
+    else act_bwd_bias_fewc_kernel<32><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(vy, vd, vz, act, dbias);
     return launched();
   }
   const int groups = cdiv(vd.c, 32);

@@ -393,8 +393,10 @@ extern "C" int segsde_conv2d_dgrad(const segsde_nhwc_t* dy, const float* w, cons
     if (rc != SEGSDE_E_UNSUPPORTED) return rc;
   }
   if (p.x1.p && (!dx2 || !dx2->ptr) && p.C2 == 0 &&
-      fewcout_ok(p.x1, p.y, p.kh, p.kw, p.stride, p.pad, false, p.nchw != 0, p.up1 != 0))
-    return fewcout_dgrad(p.y, p.x1, w, as_stream(stream));
+      fewcout_ok(p.x1, p.y, p.kh, p.kw, p.stride, p.pad, false, p.nchw != 0, p.up1 != 0)) {
+    rc = fewcout_dgrad(p.y, p.x1, w, as_stream(stream));
+    if (rc != SEGSDE_E_UNSUPPORTED) return rc;
+  }
   p.w = w; p.bias = nullptr;
   const bool refl = p.pad_mode == SEGSDE_PAD_REFLECT;
   const int off = refl ? p.pad : 0;

@@ -255,8 +255,7 @@ __global__ void head_gcol_kernel(View dy, View g, int reflect, int pad) {
   o4[1] = make_float4(v[4], v[5], v[6], v[7]);
   o4[2] = make_float4(v[8], 0.f, 0.f, 0.f);
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-  for (int k = 3; k < 8; ++k) o4[k] = zero;
+  for (int k = 3; k < (g.c >> 2); ++k) o4[k] = zero;       // 12 planes (CUDA-core heads) or 32 (tcgen05 heads)
 }
 
 }  // namespace segsde
@@ -272,7 +271,7 @@ extern "C" int segsde_head_stencil_fwd(const segsde_nhwc_t* z, const segsde_nhwc
   return launched();
 }
 extern "C" int segsde_head_gcol(const segsde_nhwc_t* dy, const segsde_nhwc_t* gcol, int reflect, int pad, void* stream) {
-  if (!dy || !gcol || !dy->ptr || !gcol->ptr || gcol->c != 32 || dy->c != 1 || pad != 1) return SEGSDE_E_ARG;
+  if (!dy || !gcol || !dy->ptr || !gcol->ptr || gcol->c < 12 || gcol->c % 4 || dy->c != 1 || pad != 1) return SEGSDE_E_ARG;
   View vd = mk(dy), vg = mk(gcol);
   if (vd.h != vg.h || vd.w != vg.w || vd.n != vg.n || !vec4_ok(vg)) return SEGSDE_E_ARG;
   const long long total = (long long)vg.n * vg.h * vg.w;

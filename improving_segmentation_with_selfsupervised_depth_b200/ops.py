@@ -26,14 +26,17 @@ PROFILE = None
 
 PROFILE_DESC = None   # optional parallel list of human-readable shapes (profiling scripts)
 # when a list, every convolution launch appends (kind, route): route = "tc:<kernel>" (kernel = conv | conv256 | rowhalo |
-# wgrad | wgrad3x3, the tcgen05 family) or "generic" (CUDA-core fallback for shapes outside the family) — tests assert on it
+# wgrad | wgrad3x3, the tcgen05 family), "cc:fewcout" (the heads' HBM-bound 1x1 GEMMs, deliberately on CUDA cores) or
+# "generic" (CUDA-core fallback for shapes outside the family) — tests assert on it
 ROUTES = None
 _TC_KERNELS = {1: "conv", 2: "rowhalo", 3: "wgrad", 4: "wgrad3x3", 5: "conv256"}
 
 
-def log_route(kind, tc):
+def log_route(kind, tc, name=None):
+    """name: a deliberate CUDA-core route ("cc:fewcout": the HBM-bound few-output-channel 1x1 GEMMs of the heads) as
+    opposed to "generic", the fallback for shapes the tcgen05 family refuses."""
     if ROUTES is not None:
-        ROUTES.append((kind, "tc:" + _TC_KERNELS.get(A.lib().segsde_tc_last_kernel(), "?") if tc else "generic"))
+        ROUTES.append((kind, name or ("tc:" + _TC_KERNELS.get(A.lib().segsde_tc_last_kernel(), "?") if tc else "generic")))
 
 
 def _timed(kind, flops, fn, desc=None):

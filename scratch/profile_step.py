@@ -1,43 +1,39 @@
-"""One profiled training step of the bench configuration: per-entry-point and per-conv breakdown."""
-import contextlib, io, sys, collections
+"""One profiled training step of a bench configuration: per-entry-point and per-conv (route, layer) breakdown.
+    python scratch/profile_step.py [dec5|dec6|joint|depthmix] [batch]"""
+import collections
+import contextlib
+import io
 import os
+import sys
+import time
+import types
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-import improving_segmentation_with_selfsupervised_depth_b200 as P
+import bench
 from improving_segmentation_with_selfsupervised_depth_b200 import _cabi as A, ops
-from improving_segmentation_with_selfsupervised_depth_b200.synthetic import MONO_LOSS_KW, mono_config, synthetic_inputs
-B, H, W = int(sys.argv[1]) if len(sys.argv) > 1 else 12, 512, 1024
-models, loss = P.install_dropin()
+name = sys.argv[1] if len(sys.argv) > 1 else "dec5"
+B = int(sys.argv[2]) if len(sys.argv) > 2 else bench.DEFAULT_BATCH[name]
+H, W = 512, 1024
 dev = torch.device('cuda')
-with contextlib.redirect_stdout(io.StringIO()):
-    model = models.get_model(mono_config('resnet50', H, W), 19).to(dev).train()
-params = [p for p in model.parameters() if p.requires_grad]
-from improving_segmentation_with_selfsupervised_depth_b200 import optim as _so
-opt = _so.Adam(params, lr=1e-4)
-ml = loss.MonodepthLoss(height=H, width=W, batch_size=B, **MONO_LOSS_KW)
-inputs = {k: v.to(dev) for k, v in synthetic_inputs(B, H, W).items()}
+args = types.SimpleNamespace(config=name, batch=B, height=H, width=W)
+model, params, task_step = bench.build_task(args, dev, 1, 0)
+inputs = {k: v.to(dev) for k, v in bench.synthetic(B, H, W, 1234, name in ("joint", "depthmix")).items()}
 def step():
-    opt.zero_grad(set_to_none=True)
     with contextlib.redirect_stdout(io.StringIO()):
-        out = model(inputs)
-    ml.generate_images_pred(inputs, out)
-    l = ml.compute_losses(inputs, out)['loss']
-    l.backward()
-    opt.step()
-for _ in range(2): step()
+        task_step(inputs)
+for _ in range(3): step()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); step(); e1.record(); torch.cuda.synchronize()
-print('unprofiled step ms', e0.elapsed_time(e1))
-import time
+print('%s B=%d unprofiled step ms' % (name, B), e0.elapsed_time(e1))
 torch.cuda.synchronize(); t0 = time.perf_counter(); step(); t1 = time.perf_counter(); torch.cuda.synchronize()
 print('host issue time of one step (queue empty, no sync inside): %.1f ms' % ((t1 - t0) * 1e3))
 A.PROFILE = []; ops.PROFILE = []; ops.PROFILE_DESC = []; ops.ROUTES = []
 e0.record(); step(); e1.record(); torch.cuda.synchronize()
 print('profiled step ms', e0.elapsed_time(e1))
 agg = collections.defaultdict(lambda: [0.0, 0])
-for name, a, b in A.PROFILE:
-    agg[name][0] += a.elapsed_time(b); agg[name][1] += 1
+for nm, a, b in A.PROFILE:
+    agg[nm][0] += a.elapsed_time(b); agg[nm][1] += 1
 tot = sum(v[0] for v in agg.values())
 print('--- by entry point (ms, calls) total %.1f' % tot)
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0]):
@@ -53,5 +49,9 @@ for ms, kind, d, tf, rt in rows:
 print('--- by (kind, route): ms, launches, TF/s')
 for k, v in sorted(byroute.items(), key=lambda kv: -kv[1][0]):
     print('%-8s %-14s %7.2f ms %4d  %7.1f TF/s' % (k[0], k[1], v[0], v[2], v[1] / (v[0] + 1e-9)))
-for ms, kind, d, tf, rt in sorted(rows, key=lambda r: -r[0])[:80]:
-    print('%7.2f ms %-6s %-12s %-44s %7.1f TF/s' % (ms, kind, rt, d, tf))
+layers = collections.defaultdict(lambda: [0.0, 0.0, 0])
+for ms, kind, d, tf, rt in rows:
+    layers[(kind, rt, d)][0] += ms; layers[(kind, rt, d)][1] += tf * ms; layers[(kind, rt, d)][2] += 1
+print('--- layers (same kind/route/shape merged): ms, launches, TF/s')
+for k, v in sorted(layers.items(), key=lambda kv: -kv[1][0])[:90]:
+    print('%7.2f ms x%-3d %-6s %-12s %-46s %7.1f TF/s' % (v[0], v[2], k[0], k[1], k[2], v[1] / (v[0] + 1e-9)))

@@ -173,11 +173,16 @@ def test_tc_conv_stride2(k, cin, cout, H, W):
     assert rel_err(gw.grad, w.grad) < TOL, "wgrad"
 
 
+@pytest.mark.parametrize("few", [True, False])
 @pytest.mark.parametrize("cin,H,W,reflect", [(64, 16, 32, True), (128, 9, 64, True), (64, 12, 32, False),
-                                             (256, 21, 96, True), (64, 2, 32, True)])
-def test_tc_disparity_head(cin, H, W, reflect):
-    """C -> 1 sigmoid heads (fwd, dgrad, wgrad, dbias): the tap-plane tensor-core GEMM + stencil route."""
+                                             (256, 21, 96, True), (64, 2, 32, True), (64, 48, 64, True),
+                                             (128, 40, 96, False)])
+def test_tc_disparity_head(cin, H, W, reflect, few, monkeypatch):
+    """C -> 1 sigmoid heads (fwd, dgrad, wgrad, dbias): tap-plane GEMMs + stencil — on the few-output-channel fp32
+    kernels (default; the two larger cases have >= 4096 pixels and reach conv_fewcout.cu) and on the tcgen05 kernels."""
     A, ops = _mods()
+    from improving_segmentation_with_selfsupervised_depth_b200 import conv_op
+    monkeypatch.setattr(conv_op, "HEAD_FEWCOUT", few)
     ops.USE_TC = True
     g = torch.Generator().manual_seed(cin + H)
     x = torch.randn(2, cin, H, W, generator=g).requires_grad_()

@@ -163,8 +163,22 @@ def test_stem_falls_back_to_im2col_for_odd_sizes(rec):
 def test_disparity_head_routes(rec, monkeypatch):
     from improving_segmentation_with_selfsupervised_depth_b200 import _cabi as A, conv_op, ops
     x, w, b = cl(2, 64, 16, 32), cl(1, 64, 3, 3), torch.zeros(1, requires_grad=True)
+    # SEGSDE_HEAD_FEWCOUT=1: 12 tap planes (9 used) through the few-output-channel CUDA-core 1x1 kernels
+    monkeypatch.setattr(conv_op, "HEAD_FEWCOUT", True)
     y = ops.conv2d(x, w, b, pad=1, pad_mode=A.PAD_REFLECT, act=A.ACT_SIGMOID)
     assert tuple(y.shape) == (2, 1, 16, 32)
+    assert rec.names() == ["segsde_copy_rows", "segsde_conv2d_fwd", "segsde_head_stencil_fwd"]
+    assert struct(rec.args_of("segsde_conv2d_fwd")[4]).c == 12
+    rec.clear()
+    y.backward(torch.ones_like(y))
+    n = rec.names()
+    assert n[0] == "segsde_act_bwd_bias" and "segsde_head_gcol" in n
+    assert n.count("segsde_conv2d_dgrad") == 1 and n.count("segsde_conv2d_wgrad") == 1
+    assert not any(k.endswith("_tc") for k in n)
+    # default: 32 planes on the tcgen05 kernels
+    rec.clear()
+    monkeypatch.setattr(conv_op, "HEAD_FEWCOUT", False)
+    y = ops.conv2d(x, w, b, pad=1, pad_mode=A.PAD_REFLECT, act=A.ACT_SIGMOID)
     assert rec.names() == ["segsde_copy_rows", "segsde_conv2d_fwd_tc", "segsde_head_stencil_fwd"]       # tap-plane route
     assert struct(rec.args_of("segsde_conv2d_fwd_tc")[4]).c == 32                                       # 9 planes padded to 32
     rec.clear()
