@@ -78,7 +78,7 @@ def dram(path, steps):
         out["reproj_dram_bytes_per_launch"] = sum(v["dram__bytes_read.sum"] + v["dram__bytes_write.sum"] for v in rp) / max(n, 1)
         out["reproj_source"] = "same capture, reproj_march_kernel<true,2>, mean of %d launches" % n
     print(json.dumps(out, indent=1))
-    sys.stderr.write("# Round 2 — DRAM traffic by kernel, %d bench steps (dec5, B=12), ncu dram__bytes_{read,write}.sum\n\n" % steps)
+    sys.stderr.write("# Round 2 — DRAM traffic by kernel, %d bench steps (B=12 dec5 unless noted), ncu dram__bytes_{read,write}.sum\n\n" % steps)
     sys.stderr.write("| kernel | launches | time ms | dram read GB | dram write GB | GB/s |\n|---|---:|---:|---:|---:|---:|\n")
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["gpu__time_duration.sum"]):
         t = v["gpu__time_duration.sum"]

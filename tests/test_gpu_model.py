@@ -227,6 +227,7 @@ def test_model_tensor_core_path_vs_oracle(contracts):
         # bounds is tests/test_gpu_tc.py; the fp32 route is checked tightly in test_network_gradients_vs_oracle).
         prev = torch.backends.cudnn.allow_tf32
         torch.backends.cudnn.allow_tf32 = True
+        torch.cuda.empty_cache()      # cuDNN's algorithm choice depends on the workspace it can get
         try:
             csd = {k: v.detach().cuda().clone().requires_grad_(v.requires_grad) for k, v in osd.items()}
             cref = O.model_forward(csd, gin, ocfg, O.BNMode(True), dropout_mask=mask.cuda())

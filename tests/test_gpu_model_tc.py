@@ -70,6 +70,8 @@ def test_train_step_tc_route_config1(backbone, H, W):
     def oracle_step(dev, tf32):
         prev = torch.backends.cudnn.allow_tf32
         torch.backends.cudnn.allow_tf32 = tf32
+        if dev == "cuda":
+            torch.cuda.empty_cache()      # cuDNN's algorithm choice depends on the workspace it can get: same start for every run
         try:
             osd = {k: v.to(dev).clone().requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in sd.items()}
             inp = {k: v.to(dev) for k, v in inputs.items()}
@@ -149,6 +151,8 @@ def test_forward_loss_512x1024_tc_route():
         def oracle(dev, tf32):
             prev = torch.backends.cudnn.allow_tf32
             torch.backends.cudnn.allow_tf32 = tf32
+            if dev == "cuda":
+                torch.cuda.empty_cache()
             try:
                 with torch.no_grad():
                     osd = {k: v.to(dev) for k, v in sd.items()}
