@@ -127,6 +127,16 @@ def cpu_threads():
     return int(os.environ.get("SEGSDE_CPU_THREADS", min(os.cpu_count() or 1, 32)))
 
 
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return "%s (%d logical CPUs)" % (line.split(":", 1)[1].strip(), os.cpu_count() or 0)
+    except OSError:
+        pass
+    return "unknown (%d logical CPUs)" % (os.cpu_count() or 0)
+
+
 def reference_trainer(config, B, H, W, seed=1234):
     """(step_fn, kind).  The reference's real Trainer over a synthetic dataset when oracle/_ref is present
     (kind "reference"); else, for dec5 only, the oracle port (kind "port")."""
@@ -209,7 +219,7 @@ def run_reference(args):
                    "name": args.config, "global_batch": args.batch * args.gpus, "parallelism": "dp%d" % args.gpus,
                    "cpu_sample": "batch %d per step (a bounded run time does not allow batch %d on the host cores); "
                                  "images/s = batch / step time" % (B, args.batch)},
-        "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": kind, "sample": sample, "cpu": cpu_model()},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 

@@ -1137,6 +1137,24 @@ extern "C" int segsde_conv2d_dgrad_tc(const segsde_nhwc_t*, const float*, const 
   return SEGSDE_E_UNSUPPORTED;
 }
 
+// Split-K factor of the weight-gradient kernels.  Every split CTA pays a prologue and a full-tile epilogue of fp32
+// atomics (a 3 x 128 x 128 tile = 196 KB of REDs, about what ten 32-pixel k-steps load), and CTAs run in waves of
+// (SMs x resident CTAs per SM): minimise  waves(s) * (chunks / s + EPI)  over s.  (Round-1 rule: 2 x SMs / ctas - two
+// waves of half-length CTAs for the one-CTA-per-SM kernel, i.e. twice the atomics for the same SM time.)
+static int pick_splits(long long ctas, long long chunks, long long maxs, int ctas_per_sm) {
+  const long long slots = (long long)num_sms() * ctas_per_sm;
+  const double EPI = 10.0;
+  long long best = 1; double best_cost = 1e30;
+  const long long smax = maxs < 4 * slots ? maxs : 4 * slots;
+  for (long long s = 1; s <= smax; ++s) {
+    const long long waves = (ctas * s + slots - 1) / slots;
+    const double per = (double)((chunks + s - 1) / s) + EPI;
+    const double cost = (double)waves * per;
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
+  }
+  return (int)best;
+}
+
 extern "C" int segsde_conv2d_wgrad_tc(const segsde_nhwc_t* x1, const segsde_nhwc_t* x2, const segsde_nhwc_t* dy,
                                       float* dw, float* dbias, const segsde_conv_desc_t* d, void* stream) {
   if (!x1 || !x1->ptr || !dy || !dy->ptr || !dw || !d) return SEGSDE_E_ARG;
@@ -1166,9 +1184,8 @@ extern "C" int segsde_conv2d_wgrad_tc(const segsde_nhwc_t* x1, const segsde_nhwc
     q.xbox = (((32 + 2 * d->dil) * 128) + 1023) / 1024 * 1024;
     q.units = ((wg64_mode() & 1) && C1 <= 64 && C2 <= 64 && d->dil == 1) ? 2 : 3;
     long long ctas = (long long)q.groups * q.units * q.ntiles;
-    long long want = (2LL * num_sms()) / ctas; if (want < 1) want = 1;
     long long maxs = q.chunks / 16; if (maxs < 1) maxs = 1;
-    q.splits = (int)(want < maxs ? want : maxs);
+    q.splits = pick_splits(ctas, q.chunks, maxs, (BN == 128 || !(wg64_mode() & 2)) ? 1 : 2);
     q.chunks_per_split = (q.chunks + q.splits - 1) / q.splits;
     q.splits = (int)((q.chunks + q.chunks_per_split - 1) / q.chunks_per_split);
     CUtensorMap x0m, x1m, x0p, x1p, dym;
@@ -1204,10 +1221,8 @@ extern "C" int segsde_conv2d_wgrad_tc(const segsde_nhwc_t* x1, const segsde_nhwc
   p.Ho = Ho; p.Wo = Wo; p.N = v1.n; p.wchunks = Wo / 32;
   p.chunks = (long long)p.N * Ho * p.wchunks;
   p.mtiles = cdiv(p.Ktot, 128); p.ntiles = Cout / BN;
-  long long want = (4LL * num_sms()) / ((long long)p.mtiles * p.ntiles);
-  if (want < 1) want = 1;
   long long maxs = p.chunks / 16; if (maxs < 1) maxs = 1;
-  p.splits = (int)(want < maxs ? want : maxs);
+  p.splits = pick_splits((long long)p.mtiles * p.ntiles, p.chunks, maxs, 2);
   p.chunks_per_split = (p.chunks + p.splits - 1) / p.splits;
   p.splits = (int)((p.chunks + p.chunks_per_split - 1) / p.chunks_per_split);
   CUtensorMap x0m, x1m, x5m, dym;

@@ -64,3 +64,15 @@ ml.generate_images_pred(inputs, out)
 ml.compute_losses(inputs, out)["loss"].backward()
 torch.cuda.synchronize()
 print("done")
+# 5. round-2 additions: the 19-class 1x1 segmentation head (few-output-channel kernels), max-pool
+xs = cl(8, 64, H, W).requires_grad_()
+wsg = (torch.randn(19, 64, 1, 1, device=dev) * 0.1).contiguous(memory_format=torch.channels_last).requires_grad_()
+for _ in range(2):
+    y = ops.conv2d(xs, wsg, torch.zeros(19, device=dev, requires_grad=True))
+    y.backward(torch.ones_like(y))
+xm = cl(B, 64, 256, 512).requires_grad_()
+for _ in range(2):
+    y = ops.maxpool3x3s2(xm)
+    y.backward(torch.ones_like(y))
+torch.cuda.synchronize()
+print("done 5")
