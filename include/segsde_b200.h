@@ -67,7 +67,10 @@ typedef struct {
 } segsde_conv_desc_t;
 
 /* y = act(conv(cat(x1[up], x2), w) + bias).  x2 may be NULL (c=0).  bias may be NULL.
- * w: [Cout][kh][kw][C1+C2] fp32.  Generic CUDA-core path: any shape. */
+ * w: [Cout][kh][kw][C1+C2] fp32.  Generic CUDA-core path: any shape.  1x1 / stride 1 / single source with
+ * 2 <= Cout <= 32, C % 4 == 0 and >= 4096 pixels (the 19-class segmentation heads,
+ * joint_segmentation_depth_decoder.py:106-107) takes the few-output-channel kernels of conv_fewcout.cu in all three
+ * directions (fwd / dgrad / wgrad below); results are fp32 either way. */
 int segsde_conv2d_fwd(const segsde_nhwc_t* x1, const segsde_nhwc_t* x2, const float* w,
                       const float* bias, const segsde_nhwc_t* y, const segsde_conv_desc_t* d,
                       void* stream);
