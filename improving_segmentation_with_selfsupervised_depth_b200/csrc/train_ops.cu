@@ -162,6 +162,14 @@ __global__ void __launch_bounds__(256) fill_ratio_kernel(const unsigned long lon
 
 // ---- T4 -------------------------------------------------------------------------------------------------------
 constexpr int MT_TENSORS = 48, MT_BLOCKS = 320, MT_CHUNK = 65536;
+// The multi-tensor kernels walk a 64K-element chunk per CTA.  When every pointer of the tensor is 16-byte aligned (chunk
+// bases are multiples of 4 elements) the chunk is walked as float4 with two vectors in flight per thread; the scalar loop
+// is the path for odd offsets and the tail.  Same per-element expression either way.  (The scalar form ran the optimizer
+// steps at 1.4 TB/s: 0.6 ms of Adam per dec5 step, 2.9 ms of SGD + clipping per joint step.)
+__device__ __forceinline__ bool al16(const void* a, const void* b = nullptr, const void* c = nullptr, const void* d = nullptr) {
+  return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) |
+           reinterpret_cast<uintptr_t>(d)) & 15) == 0;
+}
 struct MultiAxpby {
   float* dst[MT_TENSORS];
   const float* src[MT_TENSORS];
@@ -176,7 +184,20 @@ __global__ void __launch_bounds__(256) multi_axpby_kernel(const __grid_constant_
   const long long end = min(t.numel[ti], base + MT_CHUNK);
   float* __restrict__ d = t.dst[ti];
   const float* __restrict__ s = t.src[ti];
-  for (long long i = base + threadIdx.x; i < end; i += blockDim.x) d[i] = alpha * d[i] + beta * s[i];
+  long long i0 = base;
+  if (al16(d, s)) {
+    const long long n4 = (end - base) >> 2;
+    float4* d4 = reinterpret_cast<float4*>(d + base);
+    const float4* s4 = reinterpret_cast<const float4*>(s + base);
+#pragma unroll 2
+    for (long long j = threadIdx.x; j < n4; j += 256) {
+      float4 a = d4[j]; const float4 b = s4[j];
+      a.x = alpha * a.x + beta * b.x; a.y = alpha * a.y + beta * b.y; a.z = alpha * a.z + beta * b.z; a.w = alpha * a.w + beta * b.w;
+      d4[j] = a;
+    }
+    i0 = base + n4 * 4;
+  }
+  for (long long i = i0 + threadIdx.x; i < end; i += blockDim.x) d[i] = alpha * d[i] + beta * s[i];
 }
 
 static unsigned grid_for(long long n) {
@@ -295,15 +316,30 @@ __global__ void __launch_bounds__(256) multi_adam_kernel(const __grid_constant__
   float* __restrict__ p = t.p[ti]; const float* __restrict__ g = t.g[ti];
   float* __restrict__ m = t.s1[ti]; float* __restrict__ v = t.s2[ti];
   const float step_size = h.step_size;
-  for (long long i = base + threadIdx.x; i < end; i += blockDim.x) {
-    float gi = g[i];
-    const float pi = p[i];
+  auto one = [&](float& pi, float gi, float& mi, float& vi) {
     if (h.weight_decay != 0.f) gi = fmaf(h.weight_decay, pi, gi);
-    const float mi = m[i] + (gi - m[i]) * (1.f - h.beta1);                 // lerp, as torch's exp_avg.lerp_
-    const float vi = h.beta2 * v[i] + (1.f - h.beta2) * (gi * gi);
-    m[i] = mi; v[i] = vi;
+    mi = mi + (gi - mi) * (1.f - h.beta1);                                 // lerp, as torch's exp_avg.lerp_
+    vi = h.beta2 * vi + (1.f - h.beta2) * (gi * gi);
     const float denom = sqrtf(vi) / h.bias_c2_sqrt + h.eps;
-    p[i] = pi - step_size * (mi / denom);
+    pi = pi - step_size * (mi / denom);
+  };
+  long long i0 = base;
+  if (al16(p, g, m, v)) {
+    const long long n4 = (end - base) >> 2;
+    float4* p4 = reinterpret_cast<float4*>(p + base); const float4* g4 = reinterpret_cast<const float4*>(g + base);
+    float4* m4 = reinterpret_cast<float4*>(m + base); float4* v4 = reinterpret_cast<float4*>(v + base);
+#pragma unroll 2
+    for (long long j = threadIdx.x; j < n4; j += 256) {
+      float4 pp = p4[j], mm = m4[j], vv = v4[j]; const float4 gg = g4[j];
+      one(pp.x, gg.x, mm.x, vv.x); one(pp.y, gg.y, mm.y, vv.y); one(pp.z, gg.z, mm.z, vv.z); one(pp.w, gg.w, mm.w, vv.w);
+      m4[j] = mm; v4[j] = vv; p4[j] = pp;
+    }
+    i0 = base + n4 * 4;
+  }
+  for (long long i = i0 + threadIdx.x; i < end; i += blockDim.x) {
+    float pi = p[i], mi = m[i], vi = v[i];
+    one(pi, g[i], mi, vi);
+    m[i] = mi; v[i] = vi; p[i] = pi;
   }
 }
 __global__ void __launch_bounds__(256) multi_sgd_kernel(const __grid_constant__ MultiOpt t, SgdHyper h) {
@@ -311,16 +347,37 @@ __global__ void __launch_bounds__(256) multi_sgd_kernel(const __grid_constant__ 
   const long long base = (long long)t.blk_chunk[blockIdx.x] * MT_CHUNK, end = min(t.numel[ti], base + MT_CHUNK);
   float* __restrict__ p = t.p[ti]; const float* __restrict__ g = t.g[ti];
   float* __restrict__ buf = t.s1[ti];
-  for (long long i = base + threadIdx.x; i < end; i += blockDim.x) {
-    const float pi = p[i];
-    float gi = g[i];
+  const bool mom = h.momentum != 0.f;
+  auto one = [&](float& pi, float gi, float& bi) {
     if (h.weight_decay != 0.f) gi = fmaf(h.weight_decay, pi, gi);
-    if (h.momentum != 0.f) {
-      const float b = h.first ? gi : h.momentum * buf[i] + (1.f - h.dampening) * gi;
-      buf[i] = b;
+    if (mom) {
+      const float b = h.first ? gi : h.momentum * bi + (1.f - h.dampening) * gi;
+      bi = b;
       gi = h.nesterov ? gi + h.momentum * b : b;
     }
-    p[i] = pi - h.lr * gi;
+    pi = pi - h.lr * gi;
+  };
+  long long i0 = base;
+  if (al16(p, g, mom ? buf : nullptr)) {
+    const long long n4 = (end - base) >> 2;
+    float4* p4 = reinterpret_cast<float4*>(p + base); const float4* g4 = reinterpret_cast<const float4*>(g + base);
+    float4* b4 = reinterpret_cast<float4*>(buf + base);
+#pragma unroll 2
+    for (long long j = threadIdx.x; j < n4; j += 256) {
+      float4 pp = p4[j]; const float4 gg = g4[j];
+      float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (mom && !h.first) bb = b4[j];
+      one(pp.x, gg.x, bb.x); one(pp.y, gg.y, bb.y); one(pp.z, gg.z, bb.z); one(pp.w, gg.w, bb.w);
+      if (mom) b4[j] = bb;
+      p4[j] = pp;
+    }
+    i0 = base + n4 * 4;
+  }
+  for (long long i = i0 + threadIdx.x; i < end; i += blockDim.x) {
+    float pi = p[i], bi = (mom && !h.first) ? buf[i] : 0.f;
+    one(pi, g[i], bi);
+    if (mom) buf[i] = bi;
+    p[i] = pi;
   }
 }
 __global__ void __launch_bounds__(256) multi_sqnorm_kernel(const __grid_constant__ MultiOpt t, double* __restrict__ sum) {
@@ -328,7 +385,18 @@ __global__ void __launch_bounds__(256) multi_sqnorm_kernel(const __grid_constant
   const long long base = (long long)t.blk_chunk[blockIdx.x] * MT_CHUNK, end = min(t.numel[ti], base + MT_CHUNK);
   const float* __restrict__ g = t.g[ti];
   double acc = 0.0;
-  for (long long i = base + threadIdx.x; i < end; i += blockDim.x) acc += (double)g[i] * (double)g[i];
+  long long i0 = base;
+  if (al16(g)) {
+    const long long n4 = (end - base) >> 2;
+    const float4* g4 = reinterpret_cast<const float4*>(g + base);
+#pragma unroll 4
+    for (long long j = threadIdx.x; j < n4; j += 256) {
+      const float4 q = g4[j];
+      acc += (double)q.x * (double)q.x + (double)q.y * (double)q.y + (double)q.z * (double)q.z + (double)q.w * (double)q.w;
+    }
+    i0 = base + n4 * 4;
+  }
+  for (long long i = i0 + threadIdx.x; i < end; i += blockDim.x) acc += (double)g[i] * (double)g[i];
   const double s = block_sum_d(acc);
   if (threadIdx.x == 0) atomicAdd(sum, s);
 }
@@ -344,7 +412,20 @@ __global__ void __launch_bounds__(256) multi_scale_kernel(const __grid_constant_
   const long long base = (long long)t.blk_chunk[blockIdx.x] * MT_CHUNK, end = min(t.numel[ti], base + MT_CHUNK);
   float* __restrict__ g = t.g[ti];
   const float c = coef[0];
-  for (long long i = base + threadIdx.x; i < end; i += blockDim.x) g[i] *= c;
+  if (c == 1.f) return;           // gradient norm below the threshold: nothing to rewrite
+  long long i0 = base;
+  if (al16(g)) {
+    const long long n4 = (end - base) >> 2;
+    float4* g4 = reinterpret_cast<float4*>(g + base);
+#pragma unroll 4
+    for (long long j = threadIdx.x; j < n4; j += 256) {
+      float4 q = g4[j];
+      q.x *= c; q.y *= c; q.z *= c; q.w *= c;
+      g4[j] = q;
+    }
+    i0 = base + n4 * 4;
+  }
+  for (long long i = i0 + threadIdx.x; i < end; i += blockDim.x) g[i] *= c;
 }
 
 // GradScaler.unscale_ (torch._amp_foreach_non_finite_check_and_unscale_): g *= 1 / scale[0]; found_inf[0] = 1 when any
