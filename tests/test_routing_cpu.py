@@ -83,6 +83,58 @@ def test_decoder_block_with_upsampled_skip(rec):
     assert w.grad.stride() == w.stride() and b.grad.shape == (128,)
 
 
+def test_skipless_upconv_runs_as_four_phase_convolutions(rec, monkeypatch):
+    """upsample -> ReflectionPad2d(1) -> Conv3x3 without a skip (depth_decoder.py:93-100, the 64 -> 64 layer): four 2x2
+    convolutions on windows of the replicate-padded LOW-res input, each writing one [a::2, b::2] phase of y; backward =
+    four 2x2 dgrads + one fold, four wgrads + one weight fold.  SEGSDE_PHASE_UPCONV=0 restores pad_prep + 3x3."""
+    from improving_segmentation_with_selfsupervised_depth_b200 import _cabi as A, conv_op, ops
+    x, w, b = cl(2, 64, 8, 32), cl(64, 64, 3, 3), torch.zeros(64, requires_grad=True)
+    y = ops.conv2d(x, w, b, pad=1, pad_mode=A.PAD_REFLECT, up1=True, act=A.ACT_ELU)
+    assert tuple(y.shape) == (2, 64, 16, 64)
+    n = rec.names()
+    assert n[0] == "segsde_pad_replicate" and n.count("segsde_weight_phase_up") == 4 and n.count("segsde_conv2d_fwd_tc") == 4
+    assert "segsde_pad_prep" not in n
+    xp = struct(rec.args_of("segsde_pad_replicate")[1])
+    assert (xp.h, xp.w, xp.c) == (10, 34, 64)                               # 1-pixel border on the low-res tensor
+    seen = set()
+    for k in range(4):
+        f = rec.args_of("segsde_conv2d_fwd_tc", k)
+        v1, vy, d = struct(f[0]), struct(f[4]), struct(f[5])
+        assert (d.kh, d.kw, d.stride, d.pad, d.act) == (2, 2, 1, 0, A.ACT_ELU)
+        assert (v1.h, v1.w) == (9, 33) and (vy.h, vy.w, vy.c) == (8, 32, 64)
+        assert vy.sw == 2 * 64 and vy.sh == 2 * 64 * 64                     # a stride-2 phase view of the 16 x 64 output
+        seen.add(vy.ptr)
+    assert len(seen) == 4                                                   # four different phases
+    rec.clear()
+    y.backward(torch.ones_like(y))
+    n = rec.names()
+    assert n[0] == "segsde_act_bwd_bias"
+    assert n.count("segsde_conv2d_fwd_tc") == 4 and n.count("segsde_phase_up_fold") == 1      # dgrad
+    assert n.count("segsde_conv2d_wgrad_tc") == 4 and n.count("segsde_weight_phase_up_fold") == 1
+    assert "segsde_pad_fold" not in n
+    assert x.grad.shape == x.shape and w.grad.shape == w.shape and w.grad.stride() == w.stride()
+    # the switch
+    rec.clear()
+    monkeypatch.setattr(conv_op, "PHASE_UPCONV", False)
+    ops.conv2d(x, w, b, pad=1, pad_mode=A.PAD_REFLECT, up1=True, act=A.ACT_ELU)
+    assert rec.names() == ["segsde_pad_prep", "segsde_conv2d_fwd_tc"]
+
+
+def test_second_backward_over_a_retained_graph_reuses_the_flipped_weights(rec):
+    """train.py:486 (`backward(retain_graph=True)`) then :510: the transposed / tap-flipped dgrad weights stay on the
+    graph node, so the second traversal launches no second flip."""
+    from improving_segmentation_with_selfsupervised_depth_b200 import ops
+    x, w = cl(2, 64, 8, 32), cl(128, 64, 3, 3)
+    y = ops.conv2d(x, w, None, pad=1)
+    rec.clear()
+    y.sum().backward(retain_graph=True)
+    assert rec.names().count("segsde_weight_transpose_flip") == 1
+    rec.clear()
+    (2 * y).sum().backward()
+    n = rec.names()
+    assert n.count("segsde_weight_transpose_flip") == 0 and n.count("segsde_conv2d_fwd_tc") == 1      # dgrad still runs
+
+
 def test_stride2_3x3_backward_rewrites(rec, monkeypatch):
     """3x3 / stride 2 (ResNet downsampling blocks): forward strided through the TMA map; backward: dgrad as four phase
     convolutions (1, 2, 2, 4 taps) of dy writing the (row, column)-parity sub-grids of dx, wgrad directly on the strided
