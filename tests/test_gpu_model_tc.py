@@ -16,7 +16,7 @@ import pytest
 import torch
 
 import segsde_oracle as O
-from helpers import LOSS_KW
+from helpers import LOSS_KW, noise_floor_retry
 
 pytestmark = pytest.mark.gpu
 
@@ -49,6 +49,7 @@ def tc_routes(ops):
 
 
 @pytest.mark.parametrize("backbone,H,W", [("resnet50", 192, 640), ("resnet101", 192, 640)])
+@noise_floor_retry
 def test_train_step_tc_route_config1(backbone, H, W):
     """BASELINE configs[0] geometry (192x640, B=2), train mode, ASPP pooling on, ResNet-50 and the ResNet-101 every
     shipped YAML uses: forward activations, the photometric loss and every parameter gradient of one step."""
@@ -129,6 +130,7 @@ def test_train_step_tc_route_config1(backbone, H, W):
     assert float(np.median(ratios)) < 1.6, float(np.median(ratios))
 
 
+@noise_floor_retry
 def test_forward_loss_512x1024_tc_route():
     """The bench geometry itself (512x1024, batch 2 so that the CPU oracle finishes in seconds): forward + photometric
     loss on the tcgen05 route vs the fp32 CPU oracle, in eval mode (running statistics) and in train mode (what bench.py
