@@ -202,18 +202,21 @@ def run_reference(args):
     torch.set_num_threads(cores)
     B, H, W = args.ref_batch, args.height, args.width
     step, kind = reference_trainer(args.config, B, H, W)
-    for _ in range(args.warmup):
+    # bounded run time: a CPU step of this workload takes ~5 s at batch 2, so at most 3 warm-up + 24 timed steps
+    # (about two minutes) whatever K / W the caller asks for; the JSON line reports what was actually run
+    n_warm, n_steps = min(args.warmup, 3), min(args.steps, 24)
+    for _ in range(n_warm):
         step()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(n_steps):
         step()
     dt = time.perf_counter() - t0
-    val = B * args.steps / dt
+    val = B * n_steps / dt
     sample = "%s: Trainer.train_step (fwd+loss+bwd+optimizer), batch %d of the batch-%d workload, %dx%d, fp32, %d threads" % (
         "unmodified reference (oracle/_ref)" if kind == "reference" else "oracle port of the reference", B, args.batch, H, W, cores)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "images/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "n_gpus": args.gpus, "steps": n_steps, "warmup": n_warm, "ms_per_step": 1e3 * dt / n_steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%s, %dx%d 3-frame, batch %d/GPU" % (WORKLOAD[args.config], H, W, args.batch),
                    "name": args.config, "global_batch": args.batch * args.gpus, "parallelism": "dp%d" % args.gpus,
